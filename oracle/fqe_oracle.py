@@ -1,0 +1,436 @@
+"""CPU oracle for the FQE Hamiltonian-application path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in vectorised numpy, the *algorithm* of the reference's
+pure-Python code path for the hot path named in BASELINE.json (string tables,
+E_ij maps, dvec gather, two-electron contraction, coefficient scatter,
+diagonal-Coulomb apply/evolve, Taylor / Chebyshev recurrences).  It is the
+checker for the CUDA product in ``openfermion-fqe_b200`` and must never be
+imported by product code: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may use it.
+
+Parity status: PINNED.  ``tests/test_oracle_pinning.py`` checks this module
+against (a) the reference's own golden vectors
+(``/root/reference/tests/unittest_data/fqe_data/*.npy`` re-exported under
+``tests/golden/`` by ``tests/golden/make_golden.py``), (b) the literal
+known-answer tables in the reference's ``tests/fci_graph_test.py`` and (c) the
+reference C library itself compiled from ``/root/reference`` into
+``oracle/_ref`` (see ``oracle/ref_harness.py``).
+
+All ``file:line`` citations are relative to ``/root/reference/src/fqe``.
+"""
+from __future__ import annotations
+
+import math
+from functools import lru_cache
+from typing import Dict, Sequence, Tuple
+
+import numpy as np
+from scipy.special import comb, factorial, jv
+
+
+# --------------------------------------------------------------------------
+# a1: strings, Z matrix, addresses   (fci_graph.py:66-96, 301-333, 401-419)
+# --------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def z_matrix(norb: int, nele: int) -> np.ndarray:
+    """Knowles-Handy Z[k,l] addressing matrix (fci_graph.py:88-95,
+    lib/fci_graph.c:27-54).  int32[nele, norb]."""
+    z = np.zeros((nele, norb), dtype=np.int32)
+    if z.size == 0:
+        return z
+    for k in range(1, nele):
+        for ll in range(k, norb - nele + k + 1):
+            acc = 0
+            for m in range(norb - ll + 1, norb - k + 1):
+                acc += comb(m, nele - k, exact=True) - comb(
+                    m - 1, nele - k - 1, exact=True)
+            z[k - 1, ll - 1] = acc
+    for ll in range(nele, norb + 1):
+        z[nele - 1, ll - 1] = ll - nele
+    z.setflags(write=False)
+    return z
+
+
+def gosper_strings(nele: int, norb: int) -> np.ndarray:
+    """All norb-bit strings with nele bits set in ascending integer order
+    (bitstring.py lexicographic_bitstring_generator; lib/bitstring.c:29-46)."""
+    n = comb(norb, nele, exact=True)
+    out = np.zeros(n, dtype=np.uint64)
+    if nele == 0:
+        return out
+    cur = (1 << nele) - 1
+    lim = 1 << norb
+    idx = 0
+    while cur < lim:
+        out[idx] = cur
+        idx += 1
+        low = cur & -cur
+        ripple = cur + low
+        cur = (((cur & ~ripple) // low) >> 1) | ripple
+    assert idx == n
+    return out
+
+
+def occupations(strings: np.ndarray, norb: int) -> np.ndarray:
+    """bool[L, norb] occupation table."""
+    s = np.asarray(strings, dtype=np.uint64)
+    return ((s[:, None] >> np.arange(norb, dtype=np.uint64)[None, :]) &
+            np.uint64(1)).astype(bool)
+
+
+def string_addresses(strings: np.ndarray, norb: int, nele: int) -> np.ndarray:
+    """Z-matrix address of each string: sum_k Z[k, o_k] over its occupied
+    orbitals o_0<o_1<...  (fci_graph.py:401-419, lib/fci_graph.c:123-134)."""
+    strings = np.asarray(strings, dtype=np.uint64)
+    if nele == 0:
+        return np.zeros(strings.shape[0], dtype=np.int64)
+    occ = occupations(strings, norb)
+    # rank of each occupied orbital inside its string
+    rank = np.cumsum(occ, axis=1) - 1
+    z = z_matrix(norb, nele).astype(np.int64)
+    orb = np.broadcast_to(np.arange(norb)[None, :], occ.shape)
+    contrib = np.where(occ, z[np.clip(rank, 0, nele - 1), orb], 0)
+    return contrib.sum(axis=1)
+
+
+def build_strings(nele: int, norb: int) -> np.ndarray:
+    """String table in Knowles-Handy address order (fci_graph.py:301-333)."""
+    lex = gosper_strings(nele, norb)
+    addr = string_addresses(lex, norb, nele)
+    out = np.zeros_like(lex)
+    out[addr] = lex
+    return out
+
+
+# --------------------------------------------------------------------------
+# a2/a3: E_ij maps and de-excitation tables (fci_graph.py:204-237, 36-63)
+# --------------------------------------------------------------------------
+def _between_mask(i: int, j: int) -> int:
+    lo, hi = (i, j) if i < j else (j, i)
+    return ((1 << hi) - 1) & ~((1 << (lo + 1)) - 1)
+
+
+def build_mapping(strings: np.ndarray, nele: int,
+                  norb: int) -> Dict[Tuple[int, int], np.ndarray]:
+    """(source, target, sign) triples of a^+_i a_j for every (i, j), sources in
+    ascending string-index order (fci_graph.py:204-237; lib/fci_graph.c:76-121).
+    sign = (-1)^(number of occupied orbitals strictly between i and j)
+    (bitstring.py:206-221)."""
+    strings = np.asarray(strings, dtype=np.uint64)
+    nstr = strings.shape[0]
+    sidx = np.arange(nstr, dtype=np.int64)
+    out: Dict[Tuple[int, int], np.ndarray] = {}
+    for i in range(norb):
+        bi = np.uint64(1 << i)
+        for j in range(norb):
+            bj = np.uint64(1 << j)
+            if i == j:
+                sel = (strings & bj) != 0
+                src = sidx[sel]
+                trip = np.stack([src, src, np.ones_like(src)], axis=1)
+            else:
+                sel = ((strings & bj) != 0) & ((strings & bi) == 0)
+                src = sidx[sel]
+                s = strings[sel]
+                tgt_str = (s | bi) & ~bj
+                tgt = string_addresses(tgt_str, norb, nele)
+                par = np.array(
+                    [bin(int(x) & _between_mask(i, j)).count("1") for x in s],
+                    dtype=np.int64)
+                sign = 1 - 2 * (par & 1)
+                trip = np.stack([src, tgt, sign], axis=1)
+            out[(i, j)] = trip.astype(np.int32).reshape(-1, 3)
+    return out
+
+
+def map_to_deexc(mappings: Dict[Tuple[int, int], np.ndarray], nstates: int,
+                 norb: int, nele: int) -> np.ndarray:
+    """By-target table dexc[target, slot] = (source, i*norb+j, sign), slots
+    filled in (i, j) row-major order (fci_graph.py:36-63)."""
+    lk = nele * (norb - nele + 1)
+    dexc = np.zeros((nstates, lk, 3), dtype=np.int32)
+    fill = np.zeros(nstates, dtype=np.int64)
+    for i in range(norb):
+        for j in range(norb):
+            m = mappings[(i, j)]
+            if m.shape[0] == 0:
+                continue
+            tgt = m[:, 1]
+            # a target appears at most once per (i, j)
+            dexc[tgt, fill[tgt], 0] = m[:, 0]
+            dexc[tgt, fill[tgt], 1] = i * norb + j
+            dexc[tgt, fill[tgt], 2] = m[:, 2]
+            fill[tgt] += 1
+    return dexc
+
+
+class OracleGraph:
+    """Restatement of FciGraph.__init__ products (fci_graph.py:108-154)."""
+
+    def __init__(self, nalpha: int, nbeta: int, norb: int):
+        self.nalpha, self.nbeta, self.norb = nalpha, nbeta, norb
+        self.lena = comb(norb, nalpha, exact=True)
+        self.lenb = comb(norb, nbeta, exact=True)
+        self.astr = build_strings(nalpha, norb)
+        self.bstr = build_strings(nbeta, norb)
+        self.alpha_map = build_mapping(self.astr, nalpha, norb)
+        self.beta_map = build_mapping(self.bstr, nbeta, norb)
+        self.dexca = map_to_deexc(self.alpha_map, self.lena, norb, nalpha)
+        self.dexcb = map_to_deexc(self.beta_map, self.lenb, norb, nbeta)
+
+
+@lru_cache(maxsize=32)
+def graph(nalpha: int, nbeta: int, norb: int) -> OracleGraph:
+    return OracleGraph(nalpha, nbeta, norb)
+
+
+# --------------------------------------------------------------------------
+# a7 / a8 / a9: dvec gather, contraction, coefficient scatter
+# --------------------------------------------------------------------------
+def dvec_spatial(g: OracleGraph, coeff: np.ndarray) -> np.ndarray:
+    """D[i,j,t,:] += sign*C[s,:] (alpha maps), D[i,j,:,t] += sign*C[:,s]
+    (beta maps)  (fqe_data.py:2209-2234)."""
+    n = g.norb
+    d = np.zeros((n, n, g.lena, g.lenb), dtype=np.complex128)
+    for i in range(n):
+        for j in range(n):
+            ma = g.alpha_map[(i, j)]
+            if ma.shape[0]:
+                d[i, j, ma[:, 1], :] += coeff[ma[:, 0], :] * ma[:, 2][:, None]
+            mb = g.beta_map[(i, j)]
+            if mb.shape[0]:
+                d[i, j, :, mb[:, 1]] += (coeff[:, mb[:, 0]] *
+                                         mb[:, 2][None, :]).T
+    return d
+
+
+def coeff_from_dvec(g: OracleGraph, dvec: np.ndarray) -> np.ndarray:
+    """out[s,:] += sign*D[i,j,t,:] with the maps of (j,i); columns for beta
+    (fqe_data.py:2309-2334)."""
+    n = g.norb
+    out = np.zeros((g.lena, g.lenb), dtype=np.complex128)
+    for i in range(n):
+        for j in range(n):
+            ma = g.alpha_map[(j, i)]
+            if ma.shape[0]:
+                np.add.at(out, (ma[:, 0], slice(None)),
+                          dvec[i, j, ma[:, 1], :] * ma[:, 2][:, None])
+            mb = g.beta_map[(j, i)]
+            if mb.shape[0]:
+                np.add.at(out, (slice(None), mb[:, 0]),
+                          dvec[i, j][:, mb[:, 1]] * mb[:, 2][None, :])
+    return out
+
+
+def fold_restricted(h1: np.ndarray, h2: np.ndarray):
+    """h2' = -moveaxis(h2,1,2); h1' = h1 - sum_k h2'[i,k,k,j]
+    (fqe_data.py:647-652, 691-693)."""
+    h2p = -np.moveaxis(np.asarray(h2, dtype=np.complex128), 1, 2)
+    h1p = np.asarray(h1, dtype=np.complex128) - np.einsum("ikkj->ij", h2p)
+    return h1p, np.ascontiguousarray(h2p)
+
+
+def sigma_restricted(g: OracleGraph, coeff: np.ndarray, h1: np.ndarray,
+                     h2: np.ndarray) -> np.ndarray:
+    """FqeData.apply((h1,h2)) by the dvec route with complex dtype, which is
+    valid for integrals of any symmetry class (fqe_data.py:653-657)."""
+    h1p, h2p = fold_restricted(h1, h2)
+    d = dvec_spatial(g, np.asarray(coeff, dtype=np.complex128))
+    out = np.einsum("ij,ijkl->kl", h1p, d)
+    n = g.norb
+    e = (h2p.reshape(n * n, n * n) @ d.reshape(n * n, -1)).reshape(d.shape)
+    out += coeff_from_dvec(g, e)
+    return out
+
+
+def sigma_one_body(g: OracleGraph, coeff: np.ndarray,
+                   h1: np.ndarray) -> np.ndarray:
+    """FqeData.apply((h1,)) (fqe_data.py:477-530)."""
+    d = dvec_spatial(g, np.asarray(coeff, dtype=np.complex128))
+    return np.einsum("ij,ijkl->kl", np.asarray(h1, dtype=np.complex128), d)
+
+
+# --------------------------------------------------------------------------
+# a10 / a11: diagonal Coulomb
+# --------------------------------------------------------------------------
+def dc_apply(g: OracleGraph, coeff: np.ndarray, diag: np.ndarray,
+             array: np.ndarray) -> np.ndarray:
+    """C[a,b] *= A[a]+B[b]+sum_{j in b} sum_{i in a}(v[i,j]+v[j,i])
+    (fqe_data.py:293-330; lib/fqe_data.c:455-524)."""
+    diag = np.asarray(diag, dtype=np.complex128)
+    v = np.asarray(array, dtype=np.complex128)
+    oa = occupations(g.astr, g.norb).astype(np.float64)
+    ob = occupations(g.bstr, g.norb).astype(np.float64)
+    a_d = oa @ diag + np.einsum("ai,ij,aj->a", oa, v, oa)
+    b_d = ob @ diag + np.einsum("bi,ij,bj->b", ob, v, ob)
+    cross = oa @ (v + v.T) @ ob.T
+    return np.asarray(coeff, dtype=np.complex128) * (cross + a_d[:, None] +
+                                                     b_d[None, :])
+
+
+def dc_evolve(g: OracleGraph, coeff: np.ndarray, diag: np.ndarray,
+              array: np.ndarray) -> np.ndarray:
+    """C[a,b] *= Aexp[a]*Bexp[b]*(prod_{i in a, j in b} e^{v[i,j]})^2
+    (fqe_data.py:363-402; lib/fqe_data.c:526-602).  Note the alpha-beta factor
+    is squared, i.e. v is treated as symmetric."""
+    de = np.exp(np.asarray(diag, dtype=np.complex128))
+    ve = np.exp(np.asarray(array, dtype=np.complex128))
+
+    def same_spin(strings):
+        out = np.ones(strings.shape[0], dtype=np.complex128)
+        occ = occupations(strings, g.norb)
+        for s in range(strings.shape[0]):
+            idx = np.nonzero(occ[s])[0]
+            val = 1.0 + 0.0j
+            for i in idx:
+                val *= de[i]
+                for j in idx:
+                    val *= ve[i, j]
+            out[s] = val
+        return out, occ
+
+    a_d, oa = same_spin(g.astr)
+    b_d, ob = same_spin(g.bstr)
+    out = np.array(coeff, dtype=np.complex128)
+    for a in range(g.lena):
+        rowprod = np.ones(g.norb, dtype=np.complex128)
+        for i in np.nonzero(oa[a])[0]:
+            rowprod *= ve[i, :]
+        for b in range(g.lenb):
+            x = 1.0 + 0.0j
+            for j in np.nonzero(ob[b])[0]:
+                x *= rowprod[j]
+            out[a, b] *= x * x * a_d[a] * b_d[b]
+    return out
+
+
+def dc_tensors(h2e: np.ndarray):
+    """DiagonalCoulomb.__init__: 2-D input -> (0, h2e); 4-D input ->
+    diag[k]=h[k,k,k,k], vij[i,j]=-h[i,j,i,j] (hamiltonians/diagonal_coulomb.py:54-72)."""
+    h2e = np.asarray(h2e)
+    n = h2e.shape[0]
+    if h2e.ndim == 2:
+        return np.zeros(n, dtype=h2e.dtype), h2e
+    diag = np.array([h2e[k, k, k, k] for k in range(n)], dtype=h2e.dtype)
+    vij = np.zeros((n, n), dtype=h2e.dtype)
+    for i in range(n):
+        for j in range(n):
+            vij[i, j] = -h2e[i, j, i, j]
+    return diag, vij
+
+
+# --------------------------------------------------------------------------
+# a12-a15: Wavefunction-level semantics on one (n, sz) sector
+# --------------------------------------------------------------------------
+def wfn_apply_restricted(g, coeff, h1, h2, e0=0.0):
+    """Wavefunction._apply_array: sigma, then += e_0*psi when |e_0|>1e-15
+    (wavefunction.py:366-399)."""
+    out = sigma_restricted(g, coeff, h1, h2)
+    if abs(e0) > 1.0e-15:
+        out = out + e0 * coeff
+    return out
+
+
+def wfn_apply_dc(g, coeff, diag, vij, e0=0.0):
+    """Wavefunction._apply_diagonal_coulomb (wavefunction.py:421-440)."""
+    out = dc_apply(g, coeff, diag, vij)
+    if abs(e0) > 1.0e-15:
+        out = out + e0 * coeff
+    return out
+
+
+def taylor(g, coeff, time, h1, h2, e0=0.0, accuracy=1.0e-15, expansion=30):
+    """apply_generated_unitary(algo='taylor') (wavefunction.py:556-568, 604-605).
+    Returns (state, nterms).  The tuple re-wrap inside the loop drops e_0
+    (fqe_decorators.py:68-73), so e_0 only enters as the final phase."""
+    ih1 = -1.0j * time * np.asarray(h1)
+    ih2 = -1.0j * time * np.asarray(h2)
+    evol = np.array(coeff, dtype=np.complex128)
+    work = np.array(coeff, dtype=np.complex128)
+    for order in range(1, expansion):
+        work = sigma_restricted(g, work, ih1, ih2)
+        c = 1.0 / factorial(order)
+        evol += c * work
+        if np.linalg.norm(work) * abs(c) < accuracy:
+            break
+    else:
+        raise RuntimeError("maximum taylor expansion limit reached")
+    if abs(e0 * time) > 1.0e-15:
+        evol = evol * np.exp(-1.0j * time * e0)
+    return evol, order
+
+
+def chebyshev(g, coeff, time, h1, h2, spec_lim: Sequence[float], e0=0.0,
+              accuracy=1.0e-15, expansion=30):
+    """apply_generated_unitary(algo='chebyshev') (wavefunction.py:570-605).
+    Here apply(hamil) carries e_0 (the Hamiltonian object itself is applied)."""
+    wprime = 0.9875
+    ascale = (spec_lim[1] - spec_lim[0]) / (2.0 * wprime)
+    eshift = -(spec_lim[0] + ascale * wprime)
+
+    def app(x):
+        return wfn_apply_restricted(g, x, h1, h2, e0)
+
+    base = np.array(coeff, dtype=np.complex128)
+    evol = base * jv(0, ascale * time)
+    minus = base.copy()
+    current = app(minus)
+    current = (current + eshift * minus) * (1.0 / ascale)
+    evol = evol + 2.0 * jv(1, ascale * time) * (-1.0j) * current
+    for order in range(2, expansion):
+        minus = minus * (-1.0)
+        minus = minus + (2.0 / ascale) * app(current)
+        minus = minus + (2.0 * eshift / ascale) * current
+        current, minus = minus, current
+        c = 2.0 * jv(order, ascale * time) * (-1.0j)**order
+        evol = evol + c * current
+        if np.linalg.norm(current) * abs(c) < accuracy:
+            break
+    else:
+        raise RuntimeError("maximum chebyshev expansion limit reached")
+    evol = evol * np.exp(eshift * time * 1.0j)
+    if abs(e0 * time) > 1.0e-15:
+        evol = evol * np.exp(-1.0j * time * e0)
+    return evol, order
+
+
+def time_evolve_restricted(g, coeff, time, h1, h2, e0=0.0):
+    """Wavefunction.time_evolve for a non-quadratic RestrictedHamiltonian:
+    Taylor, then the e_0 phase a SECOND time (wavefunction.py:1042-1052;
+    SURVEY F5)."""
+    out, nterms = taylor(g, coeff, time, h1, h2, e0)
+    if abs(e0) > 1.0e-15:
+        out = out * np.exp(-1.0j * time * e0)
+    return out, nterms
+
+
+def time_evolve_dc(g, coeff, time, diag, vij, e0=0.0):
+    """Wavefunction.time_evolve for DiagonalCoulomb: exact diagonal evolution
+    with iht tensors, then the e_0 phase (wavefunction.py:1036-1040, 1051-1052)."""
+    out = dc_evolve(g, coeff, -1.0j * time * np.asarray(diag),
+                    -1.0j * time * np.asarray(vij))
+    if abs(e0) > 1.0e-15:
+        out = out * np.exp(-1.0j * time * e0)
+    return out
+
+
+# --------------------------------------------------------------------------
+# independent check: dense matrix of H in the determinant basis
+# --------------------------------------------------------------------------
+def dense_hamiltonian(g, h1, h2, e0=0.0):
+    """Column-by-column H matrix, as tests/evolution_test.py:527-594 builds it."""
+    dim = g.lena * g.lenb
+    hmat = np.zeros((dim, dim), dtype=np.complex128)
+    for k in range(dim):
+        e = np.zeros(dim, dtype=np.complex128)
+        e[k] = 1.0
+        hmat[:, k] = wfn_apply_restricted(g, e.reshape(g.lena, g.lenb), h1, h2,
+                                          e0).reshape(-1)
+    return hmat
+
+
+def rel_err(x, ref) -> float:
+    x = np.asarray(x)
+    ref = np.asarray(ref)
+    den = np.linalg.norm(ref)
+    return float(np.linalg.norm(x - ref) / (den if den > 0 else 1.0))

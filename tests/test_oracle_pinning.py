@@ -1,0 +1,175 @@
+"""Pin the CPU oracle (oracle/fqe_oracle.py, oracle/ref_harness.py) against the
+reference: its shipped golden vectors, its literal known-answer tables and
+outputs of its public API recorded by tests/golden/make_golden.py.
+
+Tolerance: 1e-12 relative 2-norm for floating point (the path's target is 1e-10),
+exact equality for integer tables."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fqe_oracle as O
+from oracle import ref_harness as R
+
+TOL = 1e-12
+HAVE_REF = R.available()
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def shipped(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_unittest_fqe_data.npz"))
+
+
+@pytest.fixture(scope="module")
+def graphs(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_graphs.npz"))
+
+
+@pytest.fixture(scope="module")
+def api(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_api.npz"))
+
+
+def _impls():
+    out = [("numpy", O, O.graph)]
+    if HAVE_REF:
+        out.append(("ref_c", R, R.graph))
+    return out
+
+
+# ---- literal known answers from the reference's tests/fci_graph_test.py ------
+def test_string_order_is_z_address_not_integer():
+    # (N=6, n=3) table starts 7, 11, 19, 35, 13, 21
+    assert O.build_strings(3, 6)[:6].tolist() == [7, 11, 19, 35, 13, 21]
+
+
+def test_string_address_known_answer():
+    # tests/fci_graph_test.py:121  _build_string_address(4, 8, [1,2,3,7]) == 38
+    s = np.array([(1 << 1) | (1 << 2) | (1 << 3) | (1 << 7)], dtype=np.uint64)
+    assert int(O.string_addresses(s, 8, 4)[0]) == 38
+
+
+def test_maps_norb4_known_answer():
+    # tests/fci_graph_test.py:145-207 (2 alpha, 1 beta, 4 orbitals): spot values
+    g = O.graph(2, 1, 4)
+    assert g.astr.tolist() == [3, 5, 9, 6, 10, 12]
+    assert g.bstr.tolist() == [1, 2, 4, 8]
+    assert g.alpha_map[(0, 0)].tolist() == [[0, 0, 1], [1, 1, 1], [2, 2, 1]]
+    assert g.alpha_map[(0, 1)].tolist() == [[3, 1, 1], [4, 2, 1]]
+    assert g.alpha_map[(0, 2)].tolist() == [[3, 0, -1], [5, 2, 1]]
+    assert g.beta_map[(3, 0)].tolist() == [[0, 3, 1]]
+
+
+@pytest.mark.parametrize("cfg", [(2, 1, 4), (2, 3, 6), (4, 4, 8), (3, 5, 8),
+                                 (0, 2, 5), (5, 5, 10), (1, 1, 1), (3, 3, 3),
+                                 (2, 2, 7)])
+def test_graph_tables_bit_exact(graphs, cfg):
+    na, nb, norb = cfg
+    k = f"{na}_{nb}_{norb}"
+    for name, _, mk in _impls():
+        g = mk(na, nb, norb)
+        assert np.array_equal(g.astr, graphs[k + "_astr"]), name
+        assert np.array_equal(g.bstr, graphs[k + "_bstr"]), name
+        assert np.array_equal(g.dexca, graphs[k + "_dexca"]), name
+        assert np.array_equal(g.dexcb, graphs[k + "_dexcb"]), name
+        for i in range(norb):
+            for j in range(norb):
+                assert np.array_equal(g.alpha_map[(i, j)],
+                                      graphs[f"{k}_amap_{i}_{j}"]), (name, i, j)
+                assert np.array_equal(g.beta_map[(i, j)],
+                                      graphs[f"{k}_bmap_{i}_{j}"]), (name, i, j)
+
+
+# ---- the reference's shipped goldens (tests/fqe_data_test.py:268-280,443-456,522-565)
+@pytest.mark.parametrize("cfg", [(2, 3, 6), (2, 1, 4), (1, 1, 2)])
+def test_shipped_sigma_goldens(shipped, cfg):
+    na, nb, norb = cfg
+    s = f"{na:02d}{nb:02d}{norb:02d}"
+    for name, mod, mk in _impls():
+        g = mk(na, nb, norb)
+        shp = (g.lena, g.lenb)
+        c = (shipped["cr" + s] + 1j * shipped["ci" + s]).reshape(shp)
+        h1 = shipped["h1" + s].reshape((norb,) * 2)
+        h2 = shipped["h2" + s].reshape((norb,) * 4)
+
+        def ref(tag):
+            return (shipped[f"cr{s}_{tag}"] + 1j * shipped[f"ci{s}_{tag}"]).reshape(shp)
+
+        assert O.rel_err(mod.sigma_restricted(g, c, h1, h2), ref("12")) < TOL, name
+        assert O.rel_err(mod.sigma_restricted(g, c, np.zeros_like(h1), h2),
+                         ref("2")) < TOL, name
+        assert O.rel_err(mod.sigma_restricted(g, c, h1, np.zeros_like(h2)),
+                         ref("1")) < TOL, name
+    assert O.rel_err(O.sigma_one_body(O.graph(na, nb, norb), c, h1), ref("1")) < TOL
+
+
+@pytest.mark.parametrize("cfg", [(2, 3, 6), (2, 1, 4)])
+def test_shipped_dc_evolve_golden(shipped, cfg):
+    na, nb, norb = cfg
+    s = f"{na:02d}{nb:02d}{norb:02d}"
+    for name, mod, mk in _impls():
+        g = mk(na, nb, norb)
+        shp = (g.lena, g.lenb)
+        c = (shipped["cr" + s] + 1j * shipped["ci" + s]).reshape(shp)
+        dmat = shipped["dmat" + s].reshape(norb, norb)
+        ref = (shipped[f"cr{s}_dc"] + 1j * shipped[f"ci{s}_dc"]).reshape(shp)
+        out = mod.dc_evolve(g, c, np.zeros(norb), -0.1j * dmat)
+        assert O.rel_err(out, ref) < TOL, name
+
+
+# ---- outputs of the reference public API -----------------------------------------
+@pytest.mark.parametrize("tag", list("abcde"))
+def test_api_goldens(api, tag):
+    n, sz, norb = [int(x) for x in api[f"{tag}_meta"]]
+    na, nb = (n + sz) // 2, (n - sz) // 2
+    e0 = complex(api[f"{tag}_e0"][0])
+    t = float(api[f"{tag}_t"][0])
+    h1, h2, c0 = api[f"{tag}_h1"], api[f"{tag}_h2"], api[f"{tag}_c0"]
+    vij = api[f"{tag}_vij"]
+    for name, mod, mk in _impls():
+        g = mk(na, nb, norb)
+        assert O.rel_err(mod.sigma_restricted(g, c0, h1, h2), api[f"{tag}_sigma"]) < TOL, name
+        assert O.rel_err(mod.dc_apply(g, c0, np.zeros(norb), vij) + e0 * c0,
+                         api[f"{tag}_dc_apply"]) < TOL, name
+        ev = mod.dc_evolve(g, c0, np.zeros(norb), -0.1j * vij) * np.exp(-0.1j * e0)
+        assert O.rel_err(ev, api[f"{tag}_dc_evolve"]) < TOL, name
+    g = O.graph(na, nb, norb)
+    assert O.rel_err(O.wfn_apply_restricted(g, c0, h1, h2, e0), api[f"{tag}_apply"]) < TOL
+    d4, v4 = O.dc_tensors(-np.einsum("ij,ik,jl->ijkl", vij, np.eye(norb), np.eye(norb)))
+    assert O.rel_err(O.wfn_apply_dc(g, c0, d4, v4), api[f"{tag}_dc4_apply"]) < TOL
+    assert O.rel_err(O.time_evolve_dc(g, c0, 0.1, np.zeros(norb), vij, e0),
+                     api[f"{tag}_dc_evolve"]) < TOL
+    if f"{tag}_evolve" in api:
+        out, _ = O.time_evolve_restricted(g, c0, t, h1, h2, e0)
+        assert O.rel_err(out, api[f"{tag}_evolve"]) < TOL
+        out, _ = O.taylor(g, c0, t, h1, h2, e0)
+        assert O.rel_err(out, api[f"{tag}_taylor"]) < TOL
+    if f"{tag}_cheb" in api:
+        out, _ = O.chebyshev(g, c0, t, h1, h2, list(api[f"{tag}_speclim"]), e0)
+        assert O.rel_err(out, api[f"{tag}_cheb"]) < 1e-11
+        # independent: exact exponential; taylor alone is exact, time_evolve
+        # carries the e_0 phase twice
+        assert O.rel_err(api[f"{tag}_taylor"], api[f"{tag}_exact"]) < 1e-10
+        assert O.rel_err(api[f"{tag}_evolve"],
+                         api[f"{tag}_exact"] * np.exp(-1j * t * e0)) < 1e-10
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", [(3, 3, 6), (4, 3, 7), (4, 4, 8)])
+def test_numpy_vs_ref_c_random(cfg):
+    na, nb, norb = cfg
+    rng = np.random.default_rng(77 + norb)
+    g, rg = O.graph(na, nb, norb), R.graph(na, nb, norb)
+    c = rng.standard_normal((g.lena, g.lenb)) + 1j * rng.standard_normal((g.lena, g.lenb))
+    h1 = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
+    h2 = rng.standard_normal((norb,) * 4) + 1j * rng.standard_normal((norb,) * 4)
+    assert O.rel_err(O.sigma_restricted(g, c, h1, h2), R.sigma_restricted(rg, c, h1, h2)) < TOL
+    d = O.dvec_spatial(g, c)
+    assert np.array_equal(d, R.dvec_spatial(rg, c))
+    assert O.rel_err(O.coeff_from_dvec(g, d), R.coeff_from_dvec(rg, d)) < TOL
+    diag = rng.standard_normal(norb) + 1j * rng.standard_normal(norb)
+    v = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
+    assert O.rel_err(O.dc_apply(g, c, diag, v), R.dc_apply(rg, c, diag, v)) < TOL
+    assert O.rel_err(O.dc_evolve(g, c, 0.1 * diag, 0.1 * v), R.dc_evolve(rg, c, 0.1 * diag, 0.1 * v)) < TOL
