@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark: sigma applies / s for a random RestrictedHamiltonian at
+(norb=16, n=16, Sz=0) -- BASELINE.json's metric -- on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps K --warmup W     (CPU arm)
+
+A "step" is one sigma build  sigma = H C  over the whole determinant space
+(L^2 = 165 636 900 determinants at norb=16).  One JSON line is printed by rank 0.
+
+* value      device-timed (CUDA events, max over ranks), C already resident in HBM.
+* e2e        same metric through the public API with HOST buffers: every step copies C
+             from pinned host memory to the device, prepares the operator, builds
+             sigma and copies sigma back to pinned host memory.
+* roofline   the dominant kernel is the FP64 tensor-core contraction (k_dgemm):
+             achieved = algorithmic flops of the contraction / its CUDA-event time,
+             measured live by the library's per-phase events; peak = FP64 GEMM
+             throughput of cuBLAS measured in this run (MEASURED_PEAKS.json has no
+             FP64 entry).  The HBM-bound gather / scatter phases are
+             reported against MEASURED_PEAKS.json's hbm_gbs in "phases".
+* cpu_baseline  the UNMODIFIED reference C kernels (oracle/_ref, compiled from
+             /root/reference) timed on this host's cores on exact-work samples of the
+             same norb=16 workload.
+Multi-GPU: C replicated, work sharded (--shard det|pair), one NCCL allreduce of
+sigma per step; total work is fixed, so scaling is "strong".
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "openfermion-fqe_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "sigma applies/sec (norb=16,n=16,Sz=0)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--norb", type=int, default=16)
+    ap.add_argument("--kind", default="real8", choices=["real8", "herm"],
+                    help="real8: real 8-fold symmetric integrals passed as complex128 "
+                    "(SURVEY 8d primary recipe); herm: general complex-Hermitian")
+    ap.add_argument("--shard", default="det", choices=["det", "pair"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the second operator class (complex-Hermitian) leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0,
+                    help="seconds of CPU work per reference sample")
+    return ap.parse_args()
+
+
+def metric_name(norb):
+    return METRIC if norb == 16 else f"sigma applies/sec (norb={norb},n={norb},Sz=0)"
+
+
+def workload_name(norb, kind):
+    cls = ("real 8-fold-symmetric integrals passed as complex128" if kind == "real8" else
+           "general complex-Hermitian integrals")
+    return (f"RestrictedHamiltonian sigma apply norb={norb} n={norb} Sz=0, random {cls}, "
+            f"seed=20260000+100*norb")
+
+
+# ----------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                      "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------
+# CPU arm: the reference's own C kernels on the host cores
+# ----------------------------------------------------------------------------------
+def cpu_sigma_seconds(norb, kind, budget_s):
+    from oracle import ref_harness as R
+    from fqe_b200 import synth
+    na = nb = norb // 2
+    g = R.graph(na, nb, norb)
+    h1, h2 = synth.integrals(norb, kind)
+    c = synth.state(g.lena, g.lenb, seed=synth.seed_for(norb, 50))
+    secs, desc = R.estimate_sigma_seconds(g, c, h1, h2, budget_s)
+    return secs, desc
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    times, desc = [], ""
+    # every step is one bounded exact-work sample of the full workload
+    for it in range(args.warmup + args.steps):
+        secs, desc = cpu_sigma_seconds(args.norb, args.kind, args.cpu_budget)
+        if it >= args.warmup:
+            times.append(secs)
+    mean_s = sum(times) / len(times)
+    value = 1.0 / mean_s
+    line = {
+        "impl": "reference",
+        "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * mean_s, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": workload_name(args.norb, args.kind), "norb": args.norb,
+                   "kind": args.kind},
+        "cpu_baseline": {"value": value, "unit": "sigma/s", "cores": cores, "kind": "reference",
+                         "sample": desc + "; OpenMP threads = all host cores; scipy BLAS zaxpy as "
+                         "in the reference's Cython shim"},
+        "e2e": {"value": value, "unit": "sigma/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------
+def measure_fp64_gemm_peak(torch, n=8192, reps=6):
+    """cuBLAS DGEMM burst throughput (TFLOP/s): the FP64 roofline denominator."""
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
+    """Time K sigma builds (device-resident) and, optionally, K end-to-end builds."""
+    import ctypes
+    from fqe_b200 import synth
+    from fqe_b200.distributed import shard_plan, sharded_apply
+    from fqe_b200.fqe_data import DenseOperator
+
+    norb = args.norb
+    n, sz = norb, 0
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    h1, h2 = synth.integrals(norb, kind)
+    host_c = torch.from_numpy(synth.state(la, lb, seed=synth.seed_for(norb, 50))).pin_memory()
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    sector = wfn.sector((n, sz))
+    sector.set_wfn(strategy="from_data", raw_data=host_c)
+    op = DenseOperator(norb, h1, h2)
+    rows, pairs = shard_plan(args.shard, rank, world, la, norb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return sharded_apply(sector, op, args.shard)
+
+    for _ in range(args.warmup):
+        sigma = step()
+    del sigma
+    barrier()
+    lib.fqeb_profile_enable(1)
+    ms3, cnt3 = (ctypes.c_double * 3)(), (ctypes.c_int64 * 3)()
+    lib.fqeb_profile_collect(ms3, cnt3)  # reset
+    launches0 = lib.fqeb_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        sigma = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.fqeb_launch_count() - launches0
+    lib.fqeb_profile_collect(ms3, cnt3)
+    lib.fqeb_profile_enable(0)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    checksum = float(torch.view_as_real(sigma).abs().sum().item())
+    del sigma
+
+    result = {
+        "kind": kind, "op_kind": op.kind, "ms_total": ms_max, "launches": int(launches),
+        "phase_ms": [float(x) for x in ms3], "phase_launches": [int(x) for x in cnt3],
+        "rows": rows, "pairs": pairs, "la": la, "lb": lb, "clocks": clocks,
+        "checksum": checksum,
+    }
+
+    if do_e2e:
+        host_out = torch.empty((la, lb), dtype=torch.complex128).pin_memory()
+
+        def e2e_step():
+            sector.coeff.copy_(host_c, non_blocking=True)          # H2D of this step's input
+            ham = fqe.get_restricted_hamiltonian((h1, h2))
+            op_i = wfn._dense_operator(ham.tensors())                # operator preparation
+            out = sharded_apply(sector, op_i, args.shard)
+            host_out.copy_(out, non_blocking=True)                   # D2H of the result
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        result["e2e_s"] = float(t.item())
+        result["h2d"] = host_c.numel() * 16 + h1.nbytes + h2.nbytes
+        result["d2h"] = host_out.numel() * 16
+    return result
+
+
+def run_b200(args):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+    import fqe_b200 as fqe
+    from fqe_b200 import lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    fp64_peak = measure_fp64_gemm_peak(torch)
+
+    main = run_leg(torch, dist, lib, fqe, args, args.kind, world, rank, do_e2e=True)
+    other = None
+    if not args.no_secondary:
+        other_kind = "herm" if args.kind == "real8" else "real8"
+        other = run_leg(torch, dist, lib, fqe, args, other_kind, world, rank, do_e2e=False)
+
+    def summarise(res):
+        norb = args.norb
+        npair = norb * norb
+        la, lb = res["la"], res["lb"]
+        r0, r1 = res["rows"]
+        p0, p1 = res["pairs"]
+        ndet_rank = (r1 - r0) * lb
+        cplx = res["op_kind"] == L.OP_COMPLEX
+        # algorithmic flops of the contraction on this rank, per sigma
+        flop = (8.0 if cplx else 4.0) * npair * (p1 - p0) * ndet_rank
+        k = args.steps
+        gemm_ms = res["phase_ms"][1]
+        achieved = flop * k / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # algorithmic bytes of gather / scatter: 16*(npair_slice+1) B per det
+        gat_b = 16.0 * ((p1 - p0) + 1) * ndet_rank
+        sca_b = 16.0 * (npair + 1) * ndet_rank
+        phases = {
+            "gather": {"ms_per_step": res["phase_ms"][0] / k,
+                       "GBps": gat_b * k / (res["phase_ms"][0] * 1e-3) / 1e9
+                       if res["phase_ms"][0] > 0 else 0.0},
+            "contract": {"ms_per_step": gemm_ms / k, "TFLOPs": achieved},
+            "scatter": {"ms_per_step": res["phase_ms"][2] / k,
+                        "GBps": sca_b * k / (res["phase_ms"][2] * 1e-3) / 1e9
+                        if res["phase_ms"][2] > 0 else 0.0},
+        }
+        for nm in ("gather", "scatter"):
+            phases[nm]["frac_of_hbm_peak"] = phases[nm]["GBps"] / hbm_peak
+        share = gemm_ms / max(sum(res["phase_ms"]), 1e-9)
+        return flop, achieved, phases, share
+
+    flop, achieved, phases, share = summarise(main)
+    value = args.steps / (main["ms_total"] * 1e-3)
+    line = {
+        "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_total"] / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64 DMMA)",
+        "data": "synthetic",
+        "config": {
+            "workload": workload_name(args.norb, args.kind), "norb": args.norb,
+            "determinants": main["la"] * main["lb"], "shard": args.shard,
+            "parallelism": f"{args.shard}{world}",
+            "l2": "inputs larger than L2 (C = %.2f GB, D/E chunks stream from HBM)" %
+                  (main["la"] * main["lb"] * 16 / 1e9),
+            "operator_class": {L.OP_REAL: "real", L.OP_IMAG: "imag", L.OP_COMPLEX: "complex"}[
+                main["op_kind"]],
+        },
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
+        "e2e": {"value": args.steps / main["e2e_s"], "unit": "sigma/s",
+                "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},
+        "roofline": {
+            "bound": "tensor", "kernel": "k_dgemm (FP64 DMMA contraction)",
+            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+            "flops_per_step_per_rank": flop,
+            "flop_model": ("8*norb^4*L^2 (complex h2')" if main["op_kind"] == L.OP_COMPLEX else
+                           "4*norb^4*L^2 (real h2' times complex D: 2 real FMAs per element)"),
+            "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 6, this run",
+            "share_of_step": share,
+        },
+        "phases": phases,
+        "hbm_peak": {"GBps": hbm_peak, "source": hbm_src},
+    }
+    if other is not None:
+        f2, a2, ph2, sh2 = summarise(other)
+        line["secondary"] = {
+            "workload": workload_name(args.norb, other["kind"]),
+            "value": args.steps / (other["ms_total"] * 1e-3), "unit": "sigma/s",
+            "roofline": {"achieved": a2, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": a2 / fp64_peak if fp64_peak > 0 else None,
+                         "flops_per_step_per_rank": f2, "share_of_step": sh2},
+            "phases": ph2,
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            secs, desc = cpu_sigma_seconds(args.norb, args.kind, args.cpu_budget)
+            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "sigma/s", "cores": host_cores(),
+                                    "kind": "reference", "sample": desc}
+        except Exception as exc:  # the checker is optional for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "sigma/s", "cores": host_cores(),
+                                    "kind": "reference", "sample": f"unavailable: {exc}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Build libfqe_b200.so in-tree with nvcc for sm_100a.
+
+    python openfermion-fqe_b200/build.py [--force] [--verbose]
+
+The library is a plain C-ABI shared object (see include/fqe_b200.h); it does not
+link against torch or Python.  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "fqe_b200", "lib")
+OUT = os.path.join(OUT_DIR, "libfqe_b200.so")
+SOURCES = ["core.cu", "graph.cu", "blas1.cu", "dcoulomb.cu", "dvec.cu", "dgemm.cu", "sigma.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+    "-ccbin", "/usr/bin/g++", "-Xptxas=-v", "-cudart", "static",
+]
+
+
+def stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps += [os.path.join(ROOT, "include", "fqe_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [NVCC] + FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libfqe_b200.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

@@ -1,0 +1,83 @@
+// Shared internals of libfqe_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "fqe_b200.h"
+
+namespace fqeb {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define FQEB_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t err__ = (call);                                                \
+    if (err__ != cudaSuccess) {                                                \
+      fqeb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,       \
+                      cudaGetErrorString(err__));                              \
+      return FQEB_ERR_CUDA;                                                    \
+    }                                                                          \
+  } while (0)
+
+#define FQEB_CHECK_LAUNCH()                                                    \
+  do {                                                                         \
+    cudaError_t err__ = cudaGetLastError();                                    \
+    if (err__ != cudaSuccess) {                                                \
+      fqeb::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,   \
+                      cudaGetErrorString(err__));                              \
+      return FQEB_ERR_CUDA;                                                    \
+    }                                                                          \
+    fqeb::count_launch();                                                      \
+  } while (0)
+
+#define FQEB_REQUIRE(cond, ...)                                                \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      fqeb::set_error(__VA_ARGS__);                                            \
+      return FQEB_ERR_INVALID;                                                 \
+    }                                                                          \
+  } while (0)
+
+int require_device();  // FQEB_OK or FQEB_ERR_NODEVICE (with message)
+int sm_count();
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+constexpr int kMaxOrb = 63;  // as the reference C path (settings.py c_string_max_norb)
+
+}  // namespace fqeb
+
+// ---- handle definitions -----------------------------------------------------
+struct fqeb_graph {
+  int norb, nele[2];
+  int64_t len[2];
+  int device;
+  bool shared_spin;        // nalpha == nbeta: beta tables alias alpha tables
+  int32_t *h_Z[2];         // host [nele][norb]
+  int32_t *d_Z[2];
+  uint64_t *d_str[2];      // [len]
+  // adjoint map: amap[ij][x] = sign*(y+1) with a^+_j a_i |x> = sign |y>  (ij = i*norb+j)
+  int32_t *d_amap[2];      // [norb*norb][len]
+  int32_t *d_amapT[2];     // [len][norb*norb]
+  double *d_small;         // scratch for small operator uploads (diag, v, ...)
+  size_t small_bytes;
+  double *d_sterm[2];      // per-string diagonal-Coulomb terms, complex [len]
+};
+
+struct fqeb_op {
+  int norb;
+  int kind;           // FQEB_OP_*
+  bool has_h2;
+  int device;
+  // GEMM operand: real row-major [Mp][Kp]; layout depends on kind (see dgemm.cu)
+  double *d_A;
+  int Mp, Kp;         // padded real dims of the FULL operator (all ij)
+  double *d_h1;       // complex [norb*norb] (h1' / z), interleaved
+  double zr, zi;      // global factor: 1 (real/complex) or i (imag)
+};

@@ -1,0 +1,285 @@
+// sigma = H C for a dense restricted (h1', h2') operator: the FCI sigma vector.
+//
+// Replaces FqeData._apply_array_spatial12 (reference src/fqe/fqe_data.py:582-608,
+// 644-710).  Algorithm (Knowles-Handy, the one BASELINE.json's north_star names and
+// the reference's Python branch spells out at fqe_data.py:653-657):
+//
+//     D[ij]  = E_ij C                      gather        (dvec.cu,  HBM-bound)
+//     sigma += sum_ij h1'[ij] D[ij]        fused into the gather
+//     E[kl]  = sum_ij h2'[kl,ij] D[ij]     DMMA GEMM     (dgemm.cu, FP64-bound)
+//     sigma += sum_kl E_kl^T E[kl]         scatter       (dvec.cu,  HBM-bound)
+//
+// D and E are norb^2 times larger than C (678 GB at norb=16), so the determinant
+// index is streamed in chunks of alpha rows through a caller-provided workspace;
+// all three kernels of a chunk are enqueued back-to-back on one stream.  A rank of
+// a multi-GPU job passes its shard as [row0,row1) (determinant rows) and/or
+// [ij0,ij1) (pair slice, the partition north_star mandates) and obtains a partial
+// sigma that one allreduce completes.
+#include "fqeb_common.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace fqeb {
+int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
+                     int64_t row0, int64_t nrows, int ij0, int ij1, const double *d_h1,
+                     double *d_sig, cudaStream_t st);
+int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t row0,
+                      int64_t nrows, double zr, double zi, double *d_out, cudaStream_t st);
+int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
+                    int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st);
+int dvec_rows_padded(const fqeb_op *op, int nij);
+
+// ---- optional per-phase event timing ------------------------------------------------
+struct PhaseEvent {
+  int phase;
+  cudaEvent_t start, stop;
+};
+static bool g_profile = false;
+static std::mutex g_profile_mu;
+static std::vector<PhaseEvent> g_phase_events;
+
+struct PhaseTimer {
+  bool on;
+  PhaseEvent ev;
+  cudaStream_t st;
+  PhaseTimer(int phase, cudaStream_t s) : on(g_profile), st(s) {
+    if (!on) return;
+    ev.phase = phase;
+    if (cudaEventCreate(&ev.start) != cudaSuccess || cudaEventCreate(&ev.stop) != cudaSuccess) {
+      on = false;
+      return;
+    }
+    cudaEventRecord(ev.start, st);
+  }
+  ~PhaseTimer() {
+    if (!on) return;
+    cudaEventRecord(ev.stop, st);
+    std::lock_guard<std::mutex> lock(g_profile_mu);
+    g_phase_events.push_back(ev);
+  }
+};
+
+struct ChunkLayout {
+  int64_t ldd;        // complex elements per D / E row
+  int64_t d_rows;     // rows of D (pair slice, padded)
+  int64_t e_rows;     // rows of E
+  size_t d_bytes, e_bytes;
+};
+
+static ChunkLayout layout_for(const fqeb_graph *g, const fqeb_op *op, int64_t rows, int ij0,
+                              int ij1) {
+  ChunkLayout L;
+  const int npair = g->norb * g->norb;
+  L.ldd = round_up(rows * g->len[1], fqeb_gemm_col_align());
+  L.d_rows = dvec_rows_padded(op, ij1 - ij0);
+  L.e_rows = round_up(npair, 8);
+  L.d_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.d_rows * L.ldd, 256);
+  L.e_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.e_rows * L.ldd, 256);
+  return L;
+}
+
+}  // namespace fqeb
+
+using namespace fqeb;
+
+static int check_shard(const fqeb_graph *g, const fqeb_op *op, int ij0, int ij1) {
+  FQEB_REQUIRE(g && op, "sigma: NULL handle");
+  FQEB_REQUIRE(op->norb == g->norb, "sigma: operator has %d orbitals, graph has %d", op->norb,
+               g->norb);
+  const int npair = g->norb * g->norb;
+  FQEB_REQUIRE(ij0 >= 0 && ij0 <= ij1 && ij1 <= npair, "sigma: pair slice [%d,%d) invalid", ij0,
+               ij1);
+  return FQEB_OK;
+}
+
+extern "C" size_t fqeb_sigma_workspace_bytes(const fqeb_graph *g, const fqeb_op *op,
+                                             int64_t rows_per_chunk, int ij0, int ij1) {
+  if (check_shard(g, op, ij0, ij1) != FQEB_OK || rows_per_chunk <= 0) return 0;
+  if (!op->has_h2 || ij0 == ij1) return 0;
+  const ChunkLayout L = layout_for(g, op, rows_per_chunk, ij0, ij1);
+  return L.d_bytes + L.e_bytes;
+}
+
+extern "C" int64_t fqeb_sigma_rows_for_workspace(const fqeb_graph *g, const fqeb_op *op,
+                                                 size_t bytes, int ij0, int ij1) {
+  if (check_shard(g, op, ij0, ij1) != FQEB_OK) return -1;
+  if (!op->has_h2 || ij0 == ij1) return g->len[0];
+  int64_t lo = 0, hi = g->len[0];  // largest rows with workspace_bytes(rows) <= bytes
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) / 2;
+    if (fqeb_sigma_workspace_bytes(g, op, mid, ij0, ij1) <= bytes) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
+                                     const double *d_coeff, double *d_sigma, void *d_workspace,
+                                     size_t workspace_bytes, int64_t row0, int64_t row1, int ij0,
+                                     int ij1, void *stream) {
+  int rc = require_device();
+  if (rc != FQEB_OK) return rc;
+  rc = check_shard(g, op, ij0, ij1);
+  if (rc != FQEB_OK) return rc;
+  FQEB_REQUIRE(d_coeff && d_sigma && d_coeff != d_sigma, "sigma: coeff/sigma NULL or aliased");
+  const int64_t lena = g->len[0], lenb = g->len[1];
+  FQEB_REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= lena, "sigma: row shard [%lld,%lld) invalid",
+               (long long)row0, (long long)row1);
+  cudaStream_t st = (cudaStream_t)stream;
+  FQEB_CUDA(cudaMemsetAsync(d_sigma, 0, sizeof(double) * 2 * (size_t)lena * lenb, st));
+  if (row0 == row1 || ij0 == ij1) return FQEB_OK;
+
+  if (!op->has_h2) {
+    // one-body operator: sigma = sum_ij h1[ij] D[ij], D never materialised
+    return launch_make_dvec(g, d_coeff, nullptr, 0, row0, row1 - row0, ij0, ij1, op->d_h1, d_sigma,
+                            st);
+  }
+  FQEB_REQUIRE((ij0 & 1) == 0, "sigma: pair slice must start at an even index");
+  const int64_t rows_max = fqeb_sigma_rows_for_workspace(g, op, workspace_bytes, ij0, ij1);
+  if (rows_max < 1 || d_workspace == nullptr) {
+    set_error("sigma: workspace of %zu bytes cannot hold one alpha row (need %zu)",
+              workspace_bytes, fqeb_sigma_workspace_bytes(g, op, 1, ij0, ij1));
+    return FQEB_ERR_NOMEM;
+  }
+  int64_t rows_chunk = rows_max < (row1 - row0) ? rows_max : (row1 - row0);
+  // balance the chunks so the last one is not a sliver
+  const int64_t nchunk = (row1 - row0 + rows_chunk - 1) / rows_chunk;
+  rows_chunk = (row1 - row0 + nchunk - 1) / nchunk;
+  const ChunkLayout L = layout_for(g, op, rows_chunk, ij0, ij1);
+  double *d_dvec = (double *)d_workspace;
+  double *d_evec = (double *)((char *)d_workspace + L.d_bytes);
+  const int nij = ij1 - ij0;
+  if (L.d_rows > nij) {
+    // k-padding rows of D must be exact zeros (they meet finite operator entries)
+    FQEB_CUDA(cudaMemsetAsync(d_dvec + 2 * (size_t)nij * L.ldd, 0,
+                              sizeof(double) * 2 * (size_t)(L.d_rows - nij) * L.ldd, st));
+  }
+  for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
+    const int64_t nr = (row1 - a0) < rows_chunk ? (row1 - a0) : rows_chunk;
+    {
+      PhaseTimer t(0, st);
+      rc = launch_make_dvec(g, d_coeff, d_dvec, L.ldd, a0, nr, ij0, ij1, op->d_h1, d_sigma, st);
+    }
+    if (rc != FQEB_OK) return rc;
+    {
+      PhaseTimer t(1, st);
+      rc = launch_contract(op, d_dvec, L.ldd, d_evec, L.ldd, nr * lenb, ij0, ij1, st);
+    }
+    if (rc != FQEB_OK) return rc;
+    {
+      PhaseTimer t(2, st);
+      rc = launch_make_coeff(g, d_evec, L.ldd, a0, nr, op->zr, op->zi, d_sigma, st);
+    }
+    if (rc != FQEB_OK) return rc;
+  }
+  return FQEB_OK;
+}
+
+extern "C" int fqeb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  g_profile = on != 0;
+  return FQEB_OK;
+}
+
+extern "C" int fqeb_profile_collect(double *h_ms, int64_t *h_launches) {
+  FQEB_REQUIRE(h_ms && h_launches, "fqeb_profile_collect: NULL argument");
+  for (int k = 0; k < 3; ++k) {
+    h_ms[k] = 0.0;
+    h_launches[k] = 0;
+  }
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  for (auto &ev : g_phase_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.stop) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ev.start, ev.stop) == cudaSuccess) {
+      h_ms[ev.phase] += ms;
+      h_launches[ev.phase] += 1;
+    }
+    cudaEventDestroy(ev.start);
+    cudaEventDestroy(ev.stop);
+  }
+  g_phase_events.clear();
+  return FQEB_OK;
+}
+
+// ---- host-buffer entry: the reference-facing call -----------------------------------
+namespace {
+std::mutex g_cache_mu;
+std::map<std::tuple<int, int, int, int>, fqeb_graph *> g_graph_cache;
+
+fqeb_graph *cached_graph(int norb, int na, int nb, int *rc) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  auto key = std::make_tuple(norb, na, nb, dev);
+  auto it = g_graph_cache.find(key);
+  if (it != g_graph_cache.end()) {
+    *rc = FQEB_OK;
+    return it->second;
+  }
+  fqeb_graph *g = nullptr;
+  *rc = fqeb_graph_create(norb, na, nb, &g);
+  if (*rc == FQEB_OK) g_graph_cache[key] = g;
+  return g;
+}
+}  // namespace
+
+extern "C" int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta, const double *h_h1p,
+                                          const double *h_h2p, const double *h_coeff,
+                                          double *h_sigma) {
+  int rc = require_device();
+  if (rc != FQEB_OK) return rc;
+  FQEB_REQUIRE(h_h1p && h_coeff && h_sigma, "sigma_host: NULL argument");
+  fqeb_graph *g = cached_graph(norb, nalpha, nbeta, &rc);
+  if (rc != FQEB_OK) return rc;
+  fqeb_op *op = nullptr;
+  rc = fqeb_op_create(norb, h_h1p, h_h2p, &op);
+  if (rc != FQEB_OK) return rc;
+  const size_t cbytes = sizeof(double) * 2 * (size_t)g->len[0] * g->len[1];
+  double *d_c = nullptr, *d_s = nullptr;
+  void *d_ws = nullptr;
+  size_t ws_bytes = 0;
+  auto cleanup = [&]() {
+    if (d_c) cudaFree(d_c);
+    if (d_s) cudaFree(d_s);
+    if (d_ws) cudaFree(d_ws);
+    fqeb_op_destroy(op);
+  };
+  const int npair = norb * norb;
+  if (cudaMalloc(&d_c, cbytes) != cudaSuccess || cudaMalloc(&d_s, cbytes) != cudaSuccess) {
+    set_error("sigma_host: cannot allocate coefficient buffers (%zu bytes each)", cbytes);
+    cleanup();
+    return FQEB_ERR_NOMEM;
+  }
+  if (op->has_h2) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t want = fqeb_sigma_workspace_bytes(g, op, g->len[0], 0, npair);
+    size_t budget = (size_t)(0.85 * (double)free_b);
+    ws_bytes = want < budget ? want : budget;
+    if (cudaMalloc(&d_ws, ws_bytes) != cudaSuccess) {
+      set_error("sigma_host: cannot allocate %zu-byte workspace", ws_bytes);
+      cleanup();
+      return FQEB_ERR_NOMEM;
+    }
+  }
+  cudaError_t e = cudaMemcpy(d_c, h_coeff, cbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = fqeb_sigma_restricted(g, op, d_c, d_s, d_ws, ws_bytes, 0, g->len[0], 0, npair, nullptr);
+    if (rc != FQEB_OK) {
+      cleanup();
+      return rc;
+    }
+    e = cudaMemcpy(h_sigma, d_s, cbytes, cudaMemcpyDeviceToHost);
+  }
+  if (e != cudaSuccess) {
+    set_error("sigma_host: copy failed: %s", cudaGetErrorString(e));
+    cleanup();
+    return FQEB_ERR_CUDA;
+  }
+  cleanup();
+  return FQEB_OK;
+}

@@ -1,0 +1,68 @@
+"""Multi-GPU sigma: one process per GPU, coefficient vector replicated, work sharded,
+one allreduce of sigma.
+
+Two partitions of the sigma build are supported; both leave a PARTIAL sigma of full
+size on every rank and need exactly one ``all_reduce(SUM)`` of 2*lena*lenb doubles:
+
+``pair``  the partition BASELINE.json's north_star mandates: the dvec pair index
+          ij in [0, norb^2) is split into contiguous slices; rank r gathers D for its
+          slice, contracts it against h2'[:, slice] (K = norb^2 / world) and scatters
+          all norb^2 rows of its partial E.  Gather and GEMM shrink with the world
+          size, the scatter does not.
+``det``   the alpha-row (determinant) index is split; rank r runs the complete
+          gather -> GEMM -> scatter pipeline on its rows.  All three phases shrink
+          with the world size; this is the default.
+
+The sharding arithmetic below is pure Python so it can be exercised on CPU with the
+gloo backend (tests/test_distributed_cpu.py).
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def split_even(total: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) slices of range(total) for each rank; every boundary except
+    the last is a multiple of ``align``; slices differ by at most one aligned unit."""
+    if world < 1 or total < 0 or align < 1:
+        raise ValueError("bad arguments to split_even")
+    units = (total + align - 1) // align
+    base, extra = divmod(units, world)
+    out, lo = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        hi = min(total, lo + n * align)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def shard_plan(mode: str, rank: int, world: int, lena: int, norb: int):
+    """(row_range, pair_range) of one rank."""
+    npair = norb * norb
+    if mode == "det":
+        return split_even(lena, world)[rank], (0, npair)
+    if mode == "pair":
+        # slices start at multiples of 16 pairs so that no k-padding is needed
+        return (0, lena), split_even(npair, world, align=16 if npair >= 16 * world else 2)[rank]
+    raise ValueError(f"unknown shard mode {mode!r}")
+
+
+def allreduce_sigma(sigma: torch.Tensor) -> torch.Tensor:
+    """Sum partial sigma vectors over all ranks, in place (NCCL over NVLink on GPU,
+    gloo in the CPU tests).  complex128 is reduced as float64[..., 2]."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(torch.view_as_real(sigma), op=dist.ReduceOp.SUM)
+    return sigma
+
+
+def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
+    """sigma = H C with the work of ``sector.apply_operator`` spread over the default
+    process group.  Every rank must hold the same coefficients."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sector.apply_operator(op)
+    rows, pairs = shard_plan(mode, dist.get_rank(), dist.get_world_size(), sector.lena(),
+                             sector.norb())
+    part = sector.apply_operator(op, row_range=rows, pair_range=pairs)
+    return allreduce_sigma(part)

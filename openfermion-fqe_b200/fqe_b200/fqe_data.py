@@ -1,0 +1,435 @@
+"""FqeData: one (n, sz) sector of a wavefunction, resident in HBM.
+
+Host-side mirror of the reference class (/root/reference/src/fqe/fqe_data.py:60-
+3076) for the Hamiltonian-application path.  ``coeff`` is a ``torch.complex128``
+CUDA tensor of shape ``[lena, lenb]`` (row = alpha string, column = beta string,
+C-contiguous, exactly the reference's numpy layout, fqe_data.py:106) and every
+method below forwards to a hand-written sm_100a kernel through the C ABI of
+libfqe_b200.so.  There is no CPU code path.
+
+Method names, argument meaning and error behaviour follow the reference so the
+parity tests read like its own tests (tests/fqe_data_test.py).
+"""
+import copy
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import numpy
+import torch
+
+from fqe_b200 import lib as _lib
+from fqe_b200 import settings
+from fqe_b200.fci_graph import FciGraph, get_graph
+
+_C128 = numpy.complex128
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.FqeB200Error(_lib.ERR_NODEVICE,
+                                "no CUDA device visible; fqe_b200 has no CPU fallback")
+    dev = torch.cuda.current_device()
+    _lib.call("fqeb_set_device", dev)
+    return torch.device("cuda", dev)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host_c128(arr) -> numpy.ndarray:
+    return numpy.ascontiguousarray(numpy.asarray(arr), dtype=_C128)
+
+
+def validate_config(nalpha: int, nbeta: int, norb: int) -> None:
+    """Same checks as util.validate_config in the reference (util.py)."""
+    if nalpha < 0:
+        raise ValueError("Cannot have negative number of alpha electrons")
+    if nbeta < 0:
+        raise ValueError("Cannot have negative number of beta electrons")
+    if norb < 0:
+        raise ValueError("Cannot have negative number of orbitals")
+    if norb < nalpha or norb < nbeta:
+        raise ValueError("Insufficient number of orbitals")
+
+
+# ---------------------------------------------------------------------------
+# device scratch shared by all sectors on a device
+# ---------------------------------------------------------------------------
+_SCRATCH = {}
+_WORKSPACE = {}
+_WS_CAPPED = set()
+
+
+def _reduce_scratch(dev: torch.device) -> torch.Tensor:
+    if dev not in _SCRATCH:
+        nbytes = int(_lib.load().fqeb_reduce_scratch_bytes())
+        _SCRATCH[dev] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return _SCRATCH[dev]
+
+
+def _workspace(dev: torch.device, wanted: int, minimum: int) -> torch.Tensor:
+    """A byte workspace of at most ``wanted`` and at least ``minimum`` bytes, bounded by
+    settings.workspace_fraction of the free memory.  Cached (and grown on demand) so
+    that repeated sigma builds - the Taylor loop - never reallocate."""
+    cur = _WORKSPACE.get(dev)
+    if cur is not None and (cur.numel() >= wanted or
+                            (dev in _WS_CAPPED and cur.numel() >= minimum)):
+        return cur
+    have = cur.numel() if cur is not None else 0
+    _WORKSPACE.pop(dev, None)
+    _WS_CAPPED.discard(dev)
+    del cur
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info(dev)
+    budget = int(free * settings.workspace_fraction)
+    if settings.max_workspace_bytes is not None:
+        budget = min(budget, int(settings.max_workspace_bytes))
+    size = min(wanted, max(budget, minimum, have))
+    if size < minimum:
+        raise _lib.FqeB200Error(_lib.ERR_NOMEM,
+                                f"sigma workspace needs at least {minimum} bytes, budget is {size}")
+    ws = torch.empty(size, dtype=torch.uint8, device=dev)
+    _WORKSPACE[dev] = ws
+    if size < wanted:
+        _WS_CAPPED.add(dev)   # as large as the budget allows: keep it
+    return ws
+
+
+def release_workspace() -> None:
+    """Free the cached sigma workspace (all devices)."""
+    _WORKSPACE.clear()
+    _WS_CAPPED.clear()
+    torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------
+# prepared dense operator
+# ---------------------------------------------------------------------------
+class DenseOperator:
+    """(h1, h2) folded and uploaded for repeated sigma builds.
+
+    Performs the tensor preparation of FqeData._apply_array_spatial12_lm
+    (fqe_data.py:691-693): h2' = -moveaxis(h2, 1, 2), h1' = h1 - sum_k h2'[i,k,k,j]
+    on the host (O(norb^4)), then hands both to ``fqeb_op_create``.
+    """
+
+    def __init__(self, norb: int, h1e: numpy.ndarray, h2e: Optional[numpy.ndarray] = None):
+        _require_cuda()
+        h1e = numpy.asarray(h1e)
+        if h1e.shape != (norb, norb):
+            raise ValueError(f"h1e has shape {h1e.shape}, expected {(norb, norb)}")
+        h1p = h1e.astype(_C128, copy=True)
+        h2p_ptr = None
+        self._h2p = None
+        if h2e is not None:
+            h2e = numpy.asarray(h2e)
+            if h2e.shape != (norb,) * 4:
+                raise ValueError(f"h2e has shape {h2e.shape}, expected {(norb,) * 4}")
+            h2p = numpy.ascontiguousarray(-numpy.moveaxis(h2e.astype(_C128), 1, 2))
+            h1p -= numpy.einsum("ikkj->ij", h2p)
+            self._h2p = h2p
+            h2p_ptr = h2p.ctypes.data
+        h1p = numpy.ascontiguousarray(h1p)
+        self.norb = norb
+        self.has_h2 = h2e is not None
+        handle = ctypes.c_void_p()
+        _lib.call("fqeb_op_create", norb, h1p.ctypes.data, h2p_ptr, ctypes.byref(handle))
+        self._handle = handle
+        kind = ctypes.c_int()
+        _lib.call("fqeb_op_kind", handle, ctypes.byref(kind))
+        self.kind = int(kind.value)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().fqeb_op_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+
+class FqeData:
+    """Coefficients of one sector plus the kernels that act on them."""
+
+    def __init__(self,
+                 nalpha: int,
+                 nbeta: int,
+                 norb: int,
+                 fcigraph: Optional[FciGraph] = None,
+                 dtype=numpy.complex128) -> None:
+        validate_config(nalpha, nbeta, norb)
+        if fcigraph is not None and (nalpha != fcigraph.nalpha() or nbeta != fcigraph.nbeta() or
+                                     norb != fcigraph.norb()):
+            raise ValueError("FciGraph does not match other parameters")
+        if numpy.dtype(dtype) != numpy.dtype(numpy.complex128):
+            raise TypeError("fqe_b200 stores coefficients as complex128 only")
+        dev = _require_cuda()
+        self._core = fcigraph if fcigraph is not None else get_graph(nalpha, nbeta, norb)
+        self._dtype = numpy.complex128
+        self._nele = nalpha + nbeta
+        self._m_s = nalpha - nbeta
+        self.coeff = torch.zeros((self.lena(), self.lenb()), dtype=torch.complex128, device=dev)
+
+    # ---- bookkeeping (fqe_data.py:2536-2618) ---------------------------------------
+    def get_fcigraph(self) -> FciGraph:
+        return self._core
+
+    def n_electrons(self) -> int:
+        return self._nele
+
+    def nalpha(self) -> int:
+        return self._core.nalpha()
+
+    def nbeta(self) -> int:
+        return self._core.nbeta()
+
+    def norb(self) -> int:
+        return self._core.norb()
+
+    def lena(self) -> int:
+        return self._core.lena()
+
+    def lenb(self) -> int:
+        return self._core.lenb()
+
+    def ndim(self) -> int:
+        return 2
+
+    def alpha_map(self, iorb: int, jorb: int):
+        return self._core.alpha_map(iorb, jorb)
+
+    def beta_map(self, iorb: int, jorb: int):
+        return self._core.beta_map(iorb, jorb)
+
+    def __hash__(self):
+        return hash((self._nele, self._m_s))
+
+    def __getitem__(self, key: Tuple[int, int]) -> complex:
+        return complex(self.coeff[self._core.index_alpha(key[0]),
+                                  self._core.index_beta(key[1])].item())
+
+    def __setitem__(self, key: Tuple[int, int], value: complex) -> None:
+        self.coeff[self._core.index_alpha(key[0]), self._core.index_beta(key[1])] = value
+
+    def __deepcopy__(self, memodict={}) -> 'FqeData':
+        new = self.empty_copy(zero=False)
+        new.coeff.copy_(self.coeff)
+        return new
+
+    def empty_copy(self, zero: bool = True) -> 'FqeData':
+        new = FqeData.__new__(FqeData)
+        new._core = self._core
+        new._dtype = self._dtype
+        new._nele = self._nele
+        new._m_s = self._m_s
+        new.coeff = torch.zeros_like(self.coeff) if zero else torch.empty_like(self.coeff)
+        return new
+
+    def to_numpy(self) -> numpy.ndarray:
+        """Host copy of the coefficients (numpy complex128 [lena, lenb])."""
+        return self.coeff.detach().cpu().numpy()
+
+    # ---- initialisation (fqe_data.py:2761-2810) ----------------------------------
+    def set_wfn(self, strategy: Optional[str] = None, raw_data=None) -> None:
+        strategy_args = ['ones', 'zero', 'random', 'from_data', 'hartree-fock']
+        no_data = raw_data is None or (hasattr(raw_data, "shape") and tuple(raw_data.shape) == (0,))
+        if strategy is None and no_data:
+            raise ValueError('No strategy and no data passed. Cannot initialize')
+        if strategy == 'from_data' and no_data:
+            raise ValueError('No data passed to initialize from')
+        if not no_data and strategy not in ['from_data', None]:
+            raise ValueError('Inconsistent strategy for set_vec passed with data')
+        if strategy is None:
+            strategy = 'from_data'
+        if strategy not in strategy_args:
+            raise ValueError('Unknown Argument passed to set_vec')
+        if strategy == 'from_data':
+            shape = tuple(raw_data.shape)
+            if len(shape) != 2 or shape[0] != self.lena() or shape[1] != self.lenb():
+                raise ValueError('Dim of data passed {} is not compatible with {},{}'.format(
+                    shape, self.lena(), self.lenb()))
+            if isinstance(raw_data, torch.Tensor):
+                self.coeff.copy_(raw_data.to(torch.complex128))
+            else:
+                host = torch.from_numpy(_host_c128(raw_data))
+                self.coeff.copy_(host)
+        elif strategy == 'ones':
+            self.coeff.fill_(1.0 + 0.0j)
+        elif strategy == 'zero':
+            self.coeff.zero_()
+        elif strategy == 'random':
+            # util.rand_wfn: unnormalised complex standard normal (util.py:383-397)
+            shp = (self.lena(), self.lenb())
+            host = numpy.random.randn(*shp) + 1.0j * numpy.random.randn(*shp)
+            self.coeff.copy_(torch.from_numpy(host))
+        elif strategy == 'hartree-fock':
+            self.coeff.zero_()
+            self.coeff[0, 0] = 1.0
+
+    def fill(self, value: complex) -> None:
+        self.coeff.fill_(value)
+
+    def conj(self) -> None:
+        self.coeff = torch.conj_physical(self.coeff)
+
+    # ---- BLAS-1 (fqe_data.py:2620-2632, 2701-2707, 2745-2751) -----------------------
+    def _n(self) -> int:
+        return self.coeff.numel()
+
+    def _check_coeff(self, t: torch.Tensor) -> torch.Tensor:
+        if not (t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+            raise TypeError("coefficients must be a contiguous CUDA complex128 tensor")
+        return t
+
+    def ax_plus_y(self, sval: complex, other: 'FqeData') -> 'FqeData':
+        """self.coeff += sval * other.coeff"""
+        assert hash(self) == hash(other)
+        _require_cuda()
+        sval = complex(sval)
+        _lib.call("fqeb_zaxpy", self._n(), sval.real, sval.imag,
+                  self._check_coeff(other.coeff).data_ptr(),
+                  self._check_coeff(self.coeff).data_ptr(), _stream())
+        return self
+
+    def scale(self, sval: complex) -> None:
+        _require_cuda()
+        sval = complex(sval)
+        _lib.call("fqeb_zscal", self._n(), sval.real, sval.imag,
+                  self._check_coeff(self.coeff).data_ptr(), _stream())
+
+    def norm(self) -> float:
+        dev = _require_cuda()
+        out = ctypes.c_double()
+        _lib.call("fqeb_znorm2", self._n(), self._check_coeff(self.coeff).data_ptr(),
+                  _reduce_scratch(dev).data_ptr(), ctypes.byref(out), _stream())
+        return math.sqrt(out.value)
+
+    def vdot(self, other: 'FqeData') -> complex:
+        """sum conj(self) * other (util.vdot, util.py:506-530)."""
+        dev = _require_cuda()
+        out = (ctypes.c_double * 2)()
+        _lib.call("fqeb_zdotc", self._n(), self._check_coeff(self.coeff).data_ptr(),
+                  self._check_coeff(other.coeff).data_ptr(), _reduce_scratch(dev).data_ptr(),
+                  out, _stream())
+        return complex(out[0], out[1])
+
+    def axpy_norm(self, sval: complex, work: 'FqeData') -> float:
+        """self += sval*work and return ||work|| in one pass over memory (the body of
+        the Taylor loop, wavefunction.py:563-566)."""
+        dev = _require_cuda()
+        sval = complex(sval)
+        out = ctypes.c_double()
+        _lib.call("fqeb_axpy_norm2", self._n(), sval.real, sval.imag,
+                  self._check_coeff(work.coeff).data_ptr(),
+                  self._check_coeff(self.coeff).data_ptr(), _reduce_scratch(dev).data_ptr(),
+                  ctypes.byref(out), _stream())
+        return math.sqrt(out.value)
+
+    # ---- dense operator application (fqe_data.py:404-475) -------------------------
+    def apply(self, array: Tuple[numpy.ndarray, ...]) -> 'FqeData':
+        out = copy.deepcopy(self)
+        out.apply_inplace(array)
+        return out
+
+    def apply_inplace(self, array: Tuple[numpy.ndarray, ...]) -> None:
+        len_arr = len(array)
+        if len_arr < 1 or len_arr > 4:
+            raise ValueError("Number of operators in tuple must be between 1 and 4.")
+        first = next((x for x in array if isinstance(x, numpy.ndarray)), None)
+        if first is None:
+            return
+        spatial = first.shape[0] == self.norb()
+        if not spatial and first.shape[0] != 2 * self.norb():
+            raise ValueError("Inconsistent number of spin-orbitals in operators and wavefunction.")
+        if not spatial:
+            raise NotImplementedError(
+                "fqe_b200 accelerates spatial-orbital (restricted) operators only")
+        if len_arr == 1:
+            self.coeff = self._apply_array_spatial1(array[0])
+        elif len_arr == 2:
+            self.coeff = self._apply_array_spatial12(array[0], array[1])
+        else:
+            raise NotImplementedError("3- and 4-body dense operators are outside the B200 hot path")
+
+    def apply_operator(self, op: DenseOperator, row_range=None, pair_range=None) -> torch.Tensor:
+        """sigma for a prepared operator.  ``row_range`` / ``pair_range`` restrict the
+        work to one rank's shard (partial sigma)."""
+        dev = _require_cuda()
+        if op.norb != self.norb():
+            raise ValueError("operator / wavefunction orbital mismatch")
+        npair = self.norb() * self.norb()
+        r0, r1 = row_range if row_range is not None else (0, self.lena())
+        p0, p1 = pair_range if pair_range is not None else (0, npair)
+        sigma = torch.empty_like(self.coeff)
+        ws_ptr, ws_bytes = None, 0
+        if op.has_h2 and r1 > r0 and p1 > p0:
+            lib = _lib.load()
+            wanted = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, r1 - r0,
+                                                        p0, p1))
+            minimum = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, 1, p0, p1))
+            ws = _workspace(dev, wanted, minimum)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+        _lib.call("fqeb_sigma_restricted", self._core.handle, op.handle,
+                  self._check_coeff(self.coeff).data_ptr(), sigma.data_ptr(), ws_ptr, ws_bytes,
+                  r0, r1, p0, p1, _stream())
+        return sigma
+
+    def _apply_array_spatial1(self, h1e: numpy.ndarray) -> torch.Tensor:
+        assert h1e.shape == (self.norb(), self.norb())
+        return self.apply_operator(DenseOperator(self.norb(), h1e, None))
+
+    def _apply_array_spatial12(self, h1e: numpy.ndarray, h2e: numpy.ndarray) -> torch.Tensor:
+        norb = self.norb()
+        assert h1e.shape == (norb, norb)
+        assert h2e.shape == (norb, norb, norb, norb)
+        return self.apply_operator(DenseOperator(norb, h1e, h2e))
+
+    # ---- dvec / coeff (fqe_data.py:2149-2160, 2209-2234, 2309-2334) -----------------
+    def calculate_dvec_spatial(self) -> torch.Tensor:
+        return self._calculate_dvec_spatial_with_coeff(self.coeff)
+
+    def _calculate_dvec_spatial_with_coeff(self, coeff: torch.Tensor) -> torch.Tensor:
+        dev = _require_cuda()
+        norb = self.norb()
+        dvec = torch.empty((norb, norb, self.lena(), self.lenb()), dtype=torch.complex128,
+                           device=dev)
+        _lib.call("fqeb_make_dvec", self._core.handle, self._check_coeff(coeff).data_ptr(),
+                  dvec.data_ptr(), self.lena() * self.lenb(), 0, self.lena(), 0, norb * norb,
+                  _stream())
+        return dvec
+
+    def _calculate_coeff_spatial_with_dvec(self, dvec: torch.Tensor) -> torch.Tensor:
+        dev = _require_cuda()
+        norb = self.norb()
+        if tuple(dvec.shape) != (norb, norb, self.lena(), self.lenb()):
+            raise ValueError("dvec has the wrong shape")
+        out = torch.zeros((self.lena(), self.lenb()), dtype=torch.complex128, device=dev)
+        _lib.call("fqeb_make_coeff", self._core.handle, self._check_coeff(dvec).data_ptr(),
+                  self.lena() * self.lenb(), 0, self.lena(), 1.0, 0.0, out.data_ptr(), _stream())
+        return out
+
+    # ---- diagonal Coulomb (fqe_data.py:263-402) -------------------------------------
+    def _dc(self, entry: str, diag, array, inplace: bool) -> torch.Tensor:
+        _require_cuda()
+        norb = self.norb()
+        diag = _host_c128(diag)
+        array = _host_c128(array)
+        if diag.shape != (norb,) or array.shape != (norb, norb):
+            raise ValueError("diagonal Coulomb arrays have the wrong shape")
+        data = self.coeff if inplace else self.coeff.clone()
+        _lib.call(entry, self._core.handle, diag.ctypes.data, array.ctypes.data,
+                  self._check_coeff(data).data_ptr(), _stream())
+        return data
+
+    def apply_diagonal_coulomb(self, diag, array, inplace: bool = False) -> torch.Tensor:
+        return self._dc("fqeb_dc_apply", diag, array, inplace)
+
+    def evolve_diagonal_coulomb(self, diag, array, inplace: bool = False) -> torch.Tensor:
+        return self._dc("fqeb_dc_evolve", diag, array, inplace)

@@ -1,0 +1,28 @@
+"""Global settings (counterpart of /root/reference/src/fqe/settings.py:20-51).
+
+The reference switches between a C and a pure-Python code path with
+``use_accelerated_code``.  This package has exactly one code path, CUDA on
+sm_100a, so the switch is a constant; it is kept so that code written against the
+reference's settings module keeps working.
+"""
+from enum import Enum
+
+
+class CodePath(Enum):
+    """Available code paths: CUDA only."""
+    CUDA = "cuda"
+
+
+available_code_paths = (CodePath.CUDA,)
+use_accelerated_code = True
+
+global_max_norb = 63
+"""Largest number of spatial orbitals (strings are uint64; the reference's C path
+handles 63, settings.py:47-51)."""
+
+workspace_fraction = 0.70
+"""Fraction of the free device memory the sigma build may take for its D/E chunk
+workspace when the whole D tensor does not fit."""
+
+max_workspace_bytes = None
+"""Optional hard cap (bytes) on the sigma workspace; None = no cap."""

@@ -13,6 +13,16 @@ for p in (ROOT, PKG):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# build the C-ABI library if it is missing (nvcc cross-compiles without a GPU);
+# the .so is git-ignored but travels to the GPU box with the snapshot.
+_SO = os.path.join(PKG, "fqe_b200", "lib", "libfqe_b200.so")
+if not os.path.exists(_SO):
+    import importlib.util
+    _spec = importlib.util.spec_from_file_location("fqeb_build", os.path.join(PKG, "build.py"))
+    _mod = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(_mod)
+    _mod.build()
+
 
 def pytest_configure(config):
     config.addinivalue_line(

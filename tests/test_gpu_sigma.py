@@ -1,0 +1,207 @@
+"""sigma = H C through the public API and the C ABI against the oracle, the
+reference's golden vectors and the compiled reference C path.
+
+Tolerance (BASELINE.json north_star): relative 2-norm <= 1e-10 in complex128;
+the tests assert 1e-12."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fqe_oracle as O
+from oracle import ref_harness as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _wfn(n, sz, norb, c):
+    import fqe_b200
+    w = fqe_b200.Wavefunction([[n, sz, norb]])
+    w.set_wfn(strategy="from_data", raw_data={(n, sz): c})
+    return w
+
+
+def _case(na, nb, norb, kind, seed=0):
+    from fqe_b200 import synth
+    h1, h2 = synth.integrals(norb, kind, seed=synth.seed_for(norb, seed))
+    g = O.graph(na, nb, norb)
+    c = synth.state(g.lena, g.lenb, seed=synth.seed_for(norb, seed + 50))
+    return g, c, h1, h2
+
+
+SIGMA_CFGS = [(1, 1, 2), (2, 1, 4), (2, 2, 4), (2, 3, 6), (3, 3, 6), (4, 3, 7), (4, 4, 8),
+              (0, 2, 4), (3, 0, 5), (4, 4, 4), (1, 6, 8), (5, 5, 10)]
+
+
+@pytest.mark.parametrize("cfg", SIGMA_CFGS)
+@pytest.mark.parametrize("kind", ["real8", "herm", "general"])
+def test_sigma_vs_oracle(cfg, kind):
+    na, nb, norb = cfg
+    g, c, h1, h2 = _case(na, nb, norb, kind)
+    from fqe_b200.fqe_data import FqeData
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    out = d.apply((h1, h2))
+    ref = O.sigma_restricted(g, c, h1, h2)
+    assert O.rel_err(out.to_numpy(), ref) < TOL
+    assert np.array_equal(d.to_numpy(), c)  # apply is out of place
+    # purely imaginary operator (the Taylor iht tensors) takes the real-GEMM route
+    out = d.apply((-0.05j * h1, -0.05j * h2))
+    assert O.rel_err(out.to_numpy(), -0.05j * ref) < TOL
+    # one-body only
+    out = d.apply((h1,))
+    assert O.rel_err(out.to_numpy(), O.sigma_one_body(g, c, h1)) < TOL
+
+
+def test_sigma_real_dtype_inputs():
+    """float64 tensors are accepted like the reference (pyx wrappers cast to c128)"""
+    na, nb, norb = 3, 3, 6
+    g, c, h1, h2 = _case(na, nb, norb, "real8")
+    from fqe_b200.fqe_data import FqeData
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    out = d.apply((h1.real.copy(), h2.real.copy()))
+    assert O.rel_err(out.to_numpy(), O.sigma_restricted(g, c, h1, h2)) < TOL
+
+
+@pytest.mark.parametrize("cfg", [(2, 3, 6), (2, 1, 4), (1, 1, 2)])
+def test_sigma_shipped_goldens(golden_dir, cfg):
+    """reference tests/fqe_data_test.py:443-456, 522-565 (golden _1, _2, _12)"""
+    shipped = np.load(os.path.join(golden_dir, "ref_unittest_fqe_data.npz"))
+    na, nb, norb = cfg
+    s = f"{na:02d}{nb:02d}{norb:02d}"
+    from fqe_b200.fqe_data import FqeData
+    d = FqeData(na, nb, norb)
+    shp = (d.lena(), d.lenb())
+    c = (shipped["cr" + s] + 1j * shipped["ci" + s]).reshape(shp)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    h1 = shipped["h1" + s].reshape((norb,) * 2)
+    h2 = shipped["h2" + s].reshape((norb,) * 4)
+
+    def ref(tag):
+        return (shipped[f"cr{s}_{tag}"] + 1j * shipped[f"ci{s}_{tag}"]).reshape(shp)
+
+    assert O.rel_err(d.apply((h1, h2)).to_numpy(), ref("12")) < TOL
+    assert O.rel_err(d.apply((np.zeros_like(h1), h2)).to_numpy(), ref("2")) < TOL
+    assert O.rel_err(d.apply((h1,)).to_numpy(), ref("1")) < TOL
+
+
+def test_sigma_chunked_and_sharded():
+    """small workspaces force many alpha-row chunks; row / pair shards sum to sigma"""
+    from fqe_b200 import lib as L
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    na, nb, norb = 4, 4, 8
+    for kind in ("real8", "herm"):
+        g, c, h1, h2 = _case(na, nb, norb, kind)
+        ref = O.sigma_restricted(g, c, h1, h2)
+        d = FqeData(na, nb, norb)
+        d.set_wfn(strategy="from_data", raw_data=c)
+        op = DenseOperator(norb, h1, h2)
+        lib = L.load()
+        npair = norb * norb
+        la = d.lena()
+
+        def run(rows_per_chunk, r0, r1, p0, p1):
+            nbytes = int(lib.fqeb_sigma_workspace_bytes(d._core.handle, op.handle,
+                                                        rows_per_chunk, p0, p1))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            out = torch.empty_like(d.coeff)
+            L.call("fqeb_sigma_restricted", d._core.handle, op.handle, d.coeff.data_ptr(),
+                   out.data_ptr(), ws.data_ptr(), nbytes, r0, r1, p0, p1, None)
+            torch.cuda.synchronize()
+            return out.cpu().numpy()
+
+        for rows in (1, 3, 17, la):
+            assert O.rel_err(run(rows, 0, la, 0, npair), ref) < TOL, rows
+        # determinant-row shards (world of 3)
+        parts = [run(7, r0, r1, 0, npair) for r0, r1 in [(0, 20), (20, 50), (50, la)]]
+        assert O.rel_err(sum(parts), ref) < TOL
+        # pair (ij) shards as in north_star (world of 4)
+        parts = [run(11, 0, la, p0, p1) for p0, p1 in [(0, 16), (16, 32), (32, 48), (48, 64)]]
+        assert O.rel_err(sum(parts), ref) < TOL
+        # too-small workspace is an error, not a crash
+        out = torch.empty_like(d.coeff)
+        ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+        rc = lib.fqeb_sigma_restricted(d._core.handle, op.handle, d.coeff.data_ptr(),
+                                       out.data_ptr(), ws.data_ptr(), 1024, 0, la, 0, npair, None)
+        assert rc == L.ERR_NOMEM
+
+
+def test_sigma_host_entry():
+    """the reference-facing C-ABI call with HOST buffers"""
+    from fqe_b200 import lib as L
+    from fqe_b200.fqe_data import DenseOperator
+    na, nb, norb = 3, 4, 7
+    g, c, h1, h2 = _case(na, nb, norb, "herm")
+    h1p, h2p = O.fold_restricted(h1, h2)
+    h1p = np.ascontiguousarray(h1p)
+    h2p = np.ascontiguousarray(h2p)
+    out = np.zeros_like(c)
+    cc = np.ascontiguousarray(c)
+    L.call("fqeb_sigma_restricted_host", norb, na, nb, h1p.ctypes.data, h2p.ctypes.data,
+           cc.ctypes.data, out.ctypes.data)
+    assert O.rel_err(out, O.sigma_restricted(g, c, h1, h2)) < TOL
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg,kind", [((5, 5, 10), "real8"), ((6, 6, 12), "herm"),
+                                      ((6, 5, 11), "general"), ((6, 6, 12), "real8")])
+def test_sigma_vs_compiled_reference(cfg, kind):
+    """the production C `lm` path of the reference, compiled from its sources"""
+    na, nb, norb = cfg
+    from fqe_b200 import synth
+    from fqe_b200.fqe_data import FqeData
+    h1, h2 = synth.integrals(norb, kind)
+    rg = R.graph(na, nb, norb)
+    c = synth.state(rg.lena, rg.lenb, seed=5 + norb)
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    out = d.apply((h1, h2)).to_numpy()
+    assert O.rel_err(out, R.sigma_restricted(rg, c, h1, h2)) < TOL
+
+
+def test_properties_at_full_size():
+    """size-independent checks at norb=14 (11.8M determinants), where the oracle is
+    too slow: linearity, Hermiticity <x|Hy> = <Hx|y>, the diagonal-Coulomb
+    apply == dense apply identity (reference tests/fqe_data_test.py:297-325)"""
+    import fqe_b200
+    from fqe_b200 import synth
+    norb, n, sz = 14, 14, 0
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    h1, h2 = synth.integrals(norb, "herm", scale=0.02)
+    ham = fqe_b200.get_restricted_hamiltonian((h1, h2))
+    x = fqe_b200.Wavefunction([[n, sz, norb]])
+    y = fqe_b200.Wavefunction([[n, sz, norb]])
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    for w in (x, y):
+        t = torch.randn((la, lb, 2), dtype=torch.float64, device="cuda", generator=gen)
+        w.set_wfn(strategy="from_data", raw_data={(n, sz): torch.view_as_complex(t)})
+        w.normalize()
+    hx, hy = x.apply(ham), y.apply(ham)
+    # Hermiticity
+    lhs, rhs = x.vdot(hy), hx.vdot(y)
+    assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(lhs))
+    # linearity
+    a, b = 0.3 - 0.7j, -1.1 + 0.2j
+    z = fqe_b200.Wavefunction([[n, sz, norb]])
+    z.set_wfn(strategy="zero")
+    z.ax_plus_y(a, x)
+    z.ax_plus_y(b, y)
+    hz = z.apply(ham)
+    hz.ax_plus_y(-a, hx)
+    hz.ax_plus_y(-b, hy)
+    assert hz.norm() < 1e-12 * (hx.norm() + hy.norm())
+    # diagonal Coulomb identity with a non-symmetric v
+    rng = np.random.default_rng(454417)
+    vij = 8 * rng.uniform(0, 1, size=(norb, norb)) / norb
+    h2d = np.zeros((norb,) * 4)
+    for i in range(norb):
+        for j in range(norb):
+            h2d[i, j, i, j] = -vij[i, j]
+    dense = x.apply(fqe_b200.get_restricted_hamiltonian((np.zeros((norb, norb)), h2d)))
+    diag = x.apply(fqe_b200.get_diagonalcoulomb_hamiltonian(h2d))
+    dense.ax_plus_y(-1.0, diag)
+    assert dense.norm() < 1e-12 * diag.norm()
