@@ -221,7 +221,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
     sector = wfn.sector((n, sz))
     sector.set_wfn(strategy="from_data", raw_data=host_c)
     op = DenseOperator(norb, h1, h2)
-    rows, pairs = shard_plan(args.shard, rank, world, la, norb)
+    rows, pairs = shard_plan(args.shard, rank, world, la, op.npair)
 
     def barrier():
         if world > 1:
@@ -262,7 +262,8 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
     del sigma
 
     result = {
-        "kind": kind, "op_kind": op.kind, "ms_total": ms_max, "launches": int(launches),
+        "kind": kind, "op_kind": op.kind, "op_npair": op.npair, "op_sym": op.symmetric,
+        "ms_total": ms_max, "launches": int(launches),
         "phase_ms": [float(x) for x in ms3], "phase_launches": [int(x) for x in cnt3],
         "rows": rows, "pairs": pairs, "la": la, "lb": lb, "clocks": clocks,
         "checksum": checksum,
@@ -329,8 +330,7 @@ def run_b200(args):
         other = run_leg(torch, dist, lib, fqe, args, other_kind, world, rank, do_e2e=False)
 
     def summarise(res):
-        norb = args.norb
-        npair = norb * norb
+        npair = res["op_npair"]   # pair space of the contraction (compressed if symmetric)
         la, lb = res["la"], res["lb"]
         r0, r1 = res["rows"]
         p0, p1 = res["pairs"]
@@ -373,7 +373,7 @@ def run_b200(args):
             "l2": "inputs larger than L2 (C = %.2f GB, D/E chunks stream from HBM)" %
                   (main["la"] * main["lb"] * 16 / 1e9),
             "operator_class": {L.OP_REAL: "real", L.OP_IMAG: "imag", L.OP_COMPLEX: "complex"}[
-                main["op_kind"]],
+                main["op_kind"]] + (", pair-symmetric" if main["op_sym"] else ""),
         },
         "gpu_launches": main["launches"],
         "clocks": main["clocks"],
@@ -384,8 +384,12 @@ def run_b200(args):
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
             "flops_per_step_per_rank": flop,
-            "flop_model": ("8*norb^4*L^2 (complex h2')" if main["op_kind"] == L.OP_COMPLEX else
-                           "4*norb^4*L^2 (real h2' times complex D: 2 real FMAs per element)"),
+            "flop_model": ("%d*P^2*L^2 with P=%d pairs (%s; %s)" % (
+                8 if main["op_kind"] == L.OP_COMPLEX else 4, main["op_npair"],
+                "complex h2'" if main["op_kind"] == L.OP_COMPLEX else
+                "real h2' times complex D: 2 real FMAs per element",
+                "i>=j compressed pair space, h2' pair-symmetric" if main["op_sym"] else
+                "full norb^2 pair space")),
             "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 6, this run",
             "share_of_step": share,
         },

@@ -109,6 +109,12 @@ int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p,
                    fqeb_op **out);
 int fqeb_op_destroy(fqeb_op *op);
 int fqeb_op_kind(const fqeb_op *op, int *kind);
+/* Size of the pair space the contraction runs over and whether it is compressed:
+ * norb^2, or norb(norb+1)/2 when h2p[ij,kl] == h2p[ji,kl] == h2p[ij,lk] exactly
+ * (real-orbital integrals; the compressed route of fqe_data.py:659-681).  Every
+ * [ij0, ij1) pair range of the entry points below that take an `op` refers to this
+ * space.  Set FQEB_NO_SYMMETRY=1 in the environment to disable the compression. */
+int fqeb_op_pair_space(const fqeb_op *op, int *npairs, int *symmetric);
 
 /* ------------------------------------------------------------------------
  * a7  D[i,j,a,b] = sum_I <J|a^+_i a_j|I> C_I     (gather)

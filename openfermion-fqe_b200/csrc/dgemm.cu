@@ -30,8 +30,11 @@
 //     4-stage cp.async pipeline (146 KB shared memory), k-step 16.
 //   * shared-memory strides (20 / 132 / 264 doubles) make every fragment load
 //     bank-conflict free for 64-bit accesses.
-//   * tiles are ordered M-fastest so the CTAs sharing a D tile run together and
-//     D is read from HBM once.
+//   * persistent grid (one CTA per SM) with the pipeline running across tile
+//     boundaries; tiles are ordered M-fastest so the CTAs sharing a D tile run
+//     together and D is read from HBM once.
+//   * pair-symmetric operators (real-orbital integrals) are contracted in the
+//     compressed i>=j pair space: norb(norb+1)/2 instead of norb^2 on both M and K.
 #include "fqeb_common.cuh"
 
 #include <stdlib.h>
@@ -73,27 +76,34 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // A: real row-major, leading dimension lda (doubles); a_col0 = first real k of the slice.
 // B: complex [.][ldb] (D rows of the slice start at row 0).  E: complex [.][lde].
-// m_valid: number of real rows of A that carry data (multiple of 8; of 16 for CPLX).
-// nk: number of KSTEP iterations.  npair: number of valid complex output rows.
+// m_valid: real rows of A that carry data (multiple of 8; of 16 for CPLX).
+// k_valid: real k extent of the slice (the last stage may be partial: only whole k4
+//          steps that contain data are issued; D rows / A columns beyond it are zero
+//          or meet zeros).  nrows_out: valid complex output rows.
+//
+// PERSISTENT: the grid is one CTA per SM; CTA c walks tiles c, c+grid, ... (M-fastest
+// order, so the CTAs that share a D tile run at the same time) and the cp.async
+// pipeline runs CONTINUOUSLY across tile boundaries: while the last stages of a tile
+// are in the tensor cores the first stages of the next tile are already in flight,
+// and the epilogue's stores overlap those loads.  This removes the per-tile
+// fill/drain bubble that a one-tile-per-CTA launch pays (~10% at K=256).
 template <bool CPLX>
 __global__ void __launch_bounds__(256, 1)
 k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
-        int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int npair, int nk,
-        int nmb) {
+        int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out, int k_valid,
+        int nmb, int64_t ntiles) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int wm0 = (warp >> 2) * 64;
   const int wn0 = (warp & 3) * 32;
-  const int mb = blockIdx.x % nmb;
-  const int64_t nb = blockIdx.x / nmb;
-  const int m0 = mb * BM;
-  // first determinant (complex column) of this tile
-  const int64_t n0 = nb * (CPLX ? BNR : BNR / 2);
+  const int nk = (k_valid + KSTEP - 1) / KSTEP;
+  constexpr int TILE_DETS = CPLX ? BNR : BNR / 2;
 
-  int mt_active = (m_valid - (m0 + wm0)) / 8;
-  mt_active = mt_active < 0 ? 0 : (mt_active > 8 ? 8 : mt_active);
+  if ((int64_t)blockIdx.x >= ntiles) return;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t total_it = my_tiles * nk;
 
   double acc[8][4][2];
 #pragma unroll
@@ -101,13 +111,17 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const double *Ag = A + (int64_t)m0 * lda + a_col0;
-  const double2 *Bg = B + n0;
-
-  auto load_stage = [&](int stage, int kt) {
+  // ---- producer state: (tile, kt) of the next stage to load --------------------------
+  int64_t ld_tile = blockIdx.x;
+  int ld_kt = 0;
+  auto issue_load = [&](int stage) {
+    const int mb = (int)(ld_tile % nmb);
+    const int64_t nb = ld_tile / nmb;
+    const double *Ag = A + (int64_t)(mb * BM) * lda + a_col0;
+    const double2 *Bg = B + nb * TILE_DETS;
     double *As = smem + stage * STAGE_DOUBLES;
     double *Bs = As + A_TILE;
-    const int k0 = kt * KSTEP;
+    const int k0 = ld_kt * KSTEP;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = tid + i * 256;
@@ -130,87 +144,115 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
         cp_async16(Bs + row * B_STRIDE_R + cc * 2, Bg + (int64_t)(k0 + row) * ldb + cc);
       }
     }
+    if (++ld_kt == nk) {
+      ld_kt = 0;
+      ld_tile += gridDim.x;
+    }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) load_stage(s, s);
+    if (s < total_it) issue_load(s);
     cp_async_commit();
   }
 
-  for (int kt = 0; kt < nk; ++kt) {
+  // ---- consumer state ------------------------------------------------------------------
+  int64_t tile = blockIdx.x;
+  int kt = 0;
+  int m0 = (int)(tile % nmb) * BM;
+  int mt_active = (m_valid - (m0 + wm0)) / 8;
+  mt_active = mt_active < 0 ? 0 : (mt_active > 8 ? 8 : mt_active);
+
+  for (int64_t it = 0; it < total_it; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     {
-      const int nxt = kt + STAGES - 1;
-      if (nxt < nk) load_stage(nxt % STAGES, nxt);
+      const int64_t nxt = it + STAGES - 1;
+      if (nxt < total_it) issue_load((int)(nxt % STAGES));
       cp_async_commit();
     }
-    const double *As = smem + (kt % STAGES) * STAGE_DOUBLES;
+    const double *As = smem + (int)(it % STAGES) * STAGE_DOUBLES;
     const double *Bs = As + A_TILE;
+    // whole k4 steps of this stage that contain data
+    int kk_count = (k_valid - kt * KSTEP + 3) / 4;
+    kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
 #pragma unroll
     for (int kk = 0; kk < KSTEP / 4; ++kk) {
-      double bf[4];
+      if (kk < kk_count) {
+        double bf[4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int n = wn0 + nt * 8 + g;
-        if (CPLX) {
-          bf[nt] = Bs[(kk * 2 + (tg >> 1)) * B_STRIDE_C + n * 2 + (tg & 1)];
-        } else {
-          bf[nt] = Bs[(kk * 4 + tg) * B_STRIDE_R + n];
+        for (int nt = 0; nt < 4; ++nt) {
+          const int n = wn0 + nt * 8 + g;
+          if (CPLX) {
+            bf[nt] = Bs[(kk * 2 + (tg >> 1)) * B_STRIDE_C + n * 2 + (tg & 1)];
+          } else {
+            bf[nt] = Bs[(kk * 4 + tg) * B_STRIDE_R + n];
+          }
         }
-      }
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
-        if (mt < mt_active) {
-          const double af = As[(wm0 + mt * 8 + g) * A_STRIDE + kk * 4 + tg];
+        for (int mt = 0; mt < 8; ++mt) {
+          if (mt < mt_active) {
+            const double af = As[(wm0 + mt * 8 + g) * A_STRIDE + kk * 4 + tg];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-
-  // ---- epilogue: interleaved complex128, 16-byte stores --------------------------------
-  if (CPLX) {
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (2 * p < mt_active) {
-        const int kl = ((m0 + wm0) >> 1) + p * 8 + g;
-        if (kl < npair) {
-          double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
-            erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
           }
         }
       }
     }
-  } else {
+
+    if (++kt == nk) {
+      // ---- epilogue of this tile: interleaved complex128, 16-byte stores -----------
+      const int64_t n0 = (tile / nmb) * TILE_DETS;
+      if (CPLX) {
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-      if (mt < mt_active) {
-        const int kl = m0 + wm0 + mt * 8 + g;
-        if (kl < npair) {
-          double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
+        for (int p = 0; p < 4; ++p) {
+          if (2 * p < mt_active) {
+            const int kl = ((m0 + wm0) >> 1) + p * 8 + g;
+            if (kl < nrows_out) {
+              double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
-            erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+              for (int nt = 0; nt < 4; ++nt) {
+                erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
+                erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+          if (mt < mt_active) {
+            const int kl = m0 + wm0 + mt * 8 + g;
+            if (kl < nrows_out) {
+              double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      kt = 0;
+      tile += gridDim.x;
+      m0 = (int)(tile % nmb) * BM;
+      mt_active = (m_valid - (m0 + wm0)) / 8;
+      mt_active = mt_active < 0 ? 0 : (mt_active > 8 ? 8 : mt_active);
     }
   }
+  cp_async_wait<0>();
 }
 
 static bool g_attr_set[2] = {false, false};
 
 int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
                     int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st) {
-  const int npair = op->norb * op->norb;
+  const int np = op->np;
   FQEB_REQUIRE(op->has_h2, "contract: operator has no two-body part");
-  FQEB_REQUIRE(ij0 >= 0 && ij0 < ij1 && ij1 <= npair, "contract: pair slice [%d,%d) invalid", ij0,
+  FQEB_REQUIRE(ij0 >= 0 && ij0 < ij1 && ij1 <= np, "contract: pair slice [%d,%d) invalid", ij0,
                ij1);
   FQEB_REQUIRE(ldd % COL_ALIGN == 0 && lde % COL_ALIGN == 0,
                "contract: leading dimensions must be multiples of %d", COL_ALIGN);
@@ -219,16 +261,15 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
   if (ncols == 0) return FQEB_OK;
   const bool cplx = op->kind == FQEB_OP_COMPLEX;
   const int nij = ij1 - ij0;
-  const int kslice = cplx ? 2 * nij : nij;
-  const int nk = (kslice + KSTEP - 1) / KSTEP;
+  const int k_valid = cplx ? 2 * nij : nij;
+  const int nk = (k_valid + KSTEP - 1) / KSTEP;
   const int a_col0 = cplx ? 2 * ij0 : ij0;
   FQEB_REQUIRE(a_col0 + nk * KSTEP <= op->Kp, "contract: operator padding too small");
-  const int m_valid = cplx ? 2 * (int)round_up(npair, 8) : (int)round_up(npair, 8);
+  const int m_valid = cplx ? 2 * (int)round_up(np, 8) : (int)round_up(np, 8);
   const int nmb = (m_valid + BM - 1) / BM;
   const int64_t cols_pad = round_up(ncols, COL_ALIGN);
   const int64_t nnb = cols_pad / (cplx ? BNR : BNR / 2);
   const int64_t tiles = nnb * nmb;
-  FQEB_REQUIRE(tiles < (1ll << 31), "contract: too many tiles for one launch");
   const int idx = cplx ? 1 : 0;
   if (!g_attr_set[idx]) {
     if (cplx) {
@@ -240,23 +281,33 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
     }
     g_attr_set[idx] = true;
   }
+  // persistent: one CTA per SM, rounded down to a multiple of nmb so that the CTAs
+  // sharing a D tile stay aligned
+  int64_t grid = sm_count();
+  if (grid > nmb) grid -= grid % nmb;
+  if (grid > tiles) grid = tiles;
   if (cplx) {
-    k_dgemm<true><<<(unsigned)tiles, 256, GEMM_SMEM, st>>>(
+    k_dgemm<true><<<(unsigned)grid, 256, GEMM_SMEM, st>>>(
         op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd, (double2 *)d_evec, lde, m_valid,
-        npair, nk, nmb);
+        np, k_valid, nmb, tiles);
   } else {
-    k_dgemm<false><<<(unsigned)tiles, 256, GEMM_SMEM, st>>>(
+    k_dgemm<false><<<(unsigned)grid, 256, GEMM_SMEM, st>>>(
         op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd, (double2 *)d_evec, lde, m_valid,
-        npair, nk, nmb);
+        np, k_valid, nmb, tiles);
   }
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }
 
-// rows of D a caller must provide (zero-filled beyond the slice) for a slice of nij pairs
+// rows of D a caller must allocate for a slice of nij pairs (whole pipeline stages) ...
 int dvec_rows_padded(const fqeb_op *op, int nij) {
   const bool cplx = op->kind == FQEB_OP_COMPLEX;
   return (int)round_up(nij, cplx ? KSTEP / 2 : KSTEP);
+}
+// ... of which rows [nij, this) are read by a partial k4 step and must be zero
+int dvec_rows_zeroed(const fqeb_op *op, int nij) {
+  const bool cplx = op->kind == FQEB_OP_COMPLEX;
+  return (int)round_up(nij, cplx ? 2 : 4);
 }
 
 }  // namespace fqeb
@@ -289,6 +340,8 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
   op->kind = FQEB_OP_REAL;
   op->zr = 1.0;
   op->zi = 0.0;
+  op->sym = false;
+  op->np = npair;
   cudaGetDevice(&op->device);
   auto fail = [&](int code) {
     fqeb_op_destroy(op);
@@ -300,6 +353,9 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
     set_error("fqeb_op_create: cannot upload h1: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(FQEB_ERR_CUDA);
   }
+  auto h2 = [&](int i, int j, int k, int l, int part) {
+    return h_h2p[2 * ((((size_t)i * norb + j) * norb + k) * norb + l) + part];
+  };
   if (op->has_h2) {
     const size_t n2 = (size_t)npair * npair;
     bool any_re = false, any_im = false;
@@ -313,31 +369,93 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
       op->zr = 0.0;
       op->zi = 1.0;
     }
+    // pair symmetry h2'[ij,kl] == h2'[ji,kl] == h2'[ij,lk] (exact): real-orbital
+    // integrals.  Then E[ij] == E[ji] and only i>=j pairs are contracted, against
+    // D[ij]+D[ji]: the compressed algorithm of the reference's real branch
+    // (fqe_data.py:659-681), valid here for any coefficient class.
+    bool sym = getenv("FQEB_NO_SYMMETRY") == nullptr;
+    for (int i = 0; i < norb && sym; ++i)
+      for (int j = 0; j < norb && sym; ++j)
+        for (int k = 0; k < norb && sym; ++k)
+          for (int l = 0; l < norb && sym; ++l)
+            for (int part = 0; part < 2; ++part)
+              if (h2(i, j, k, l, part) != h2(j, i, k, l, part) ||
+                  h2(i, j, k, l, part) != h2(i, j, l, k, part))
+                sym = false;
+    op->sym = sym;
+    op->np = sym ? norb * (norb + 1) / 2 : npair;
+  }
+  // pair tables
+  {
+    const int np = op->np;
+    std::vector<int32_t> tab(2 * (size_t)np + npair);
+    int32_t *pairs = tab.data(), *rowmap = tab.data() + 2 * np;
+    if (op->sym) {
+      for (int i = 0; i < norb; ++i)
+        for (int j = 0; j <= i; ++j) {
+          const int c = i * (i + 1) / 2 + j;
+          pairs[2 * c] = i * norb + j;
+          pairs[2 * c + 1] = (i == j) ? -1 : j * norb + i;
+          rowmap[i * norb + j] = c;
+          rowmap[j * norb + i] = c;
+        }
+    } else {
+      for (int p = 0; p < npair; ++p) {
+        pairs[2 * p] = p;
+        pairs[2 * p + 1] = -1;
+        rowmap[p] = p;
+      }
+    }
+    if (cudaMalloc(&op->d_pairs, sizeof(int32_t) * tab.size()) != cudaSuccess ||
+        cudaMemcpy(op->d_pairs, tab.data(), sizeof(int32_t) * tab.size(),
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("fqeb_op_create: cannot upload pair tables");
+      return fail(FQEB_ERR_CUDA);
+    }
+    op->d_rowmap = op->d_pairs + 2 * np;
+  }
+  if (op->has_h2) {
+    const int np = op->np;
+    // (row c, col d) of the contraction operand: h2'[pair(c), pair(d)]
+    auto elem = [&](int c, int d, int part) {
+      int ij, kl;
+      if (op->sym) {
+        // invert c = i(i+1)/2 + j
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= c) ++i;
+        ij = i * norb + (c - i * (i + 1) / 2);
+        int k = 0;
+        while ((k + 1) * (k + 2) / 2 <= d) ++k;
+        kl = k * norb + (d - k * (k + 1) / 2);
+      } else {
+        ij = c;
+        kl = d;
+      }
+      return h_h2p[2 * ((size_t)ij * npair + kl) + part];
+    };
     std::vector<double> a;
     if (op->kind == FQEB_OP_COMPLEX) {
-      const int np8 = (int)round_up(npair, 8);
+      const int np8 = (int)round_up(np, 8);
       op->Mp = (int)round_up(2 * np8, BM);
-      op->Kp = (int)round_up(2 * npair, KSTEP) + KSTEP;  // slack for ragged slices
+      op->Kp = (int)round_up(2 * np, KSTEP) + KSTEP;  // slack for ragged slices
       a.assign((size_t)op->Mp * op->Kp, 0.0);
-      for (int kl = 0; kl < npair; ++kl) {
-        const int rre = (kl / 8) * 16 + (kl % 8), rim = rre + 8;
-        for (int ij = 0; ij < npair; ++ij) {
-          const double re = h_h2p[2 * ((size_t)kl * npair + ij)];
-          const double im = h_h2p[2 * ((size_t)kl * npair + ij) + 1];
-          a[(size_t)rre * op->Kp + 2 * ij] = re;
-          a[(size_t)rre * op->Kp + 2 * ij + 1] = -im;
-          a[(size_t)rim * op->Kp + 2 * ij] = im;
-          a[(size_t)rim * op->Kp + 2 * ij + 1] = re;
+      for (int c = 0; c < np; ++c) {
+        const int rre = (c / 8) * 16 + (c % 8), rim = rre + 8;
+        for (int d = 0; d < np; ++d) {
+          const double re = elem(c, d, 0), im = elem(c, d, 1);
+          a[(size_t)rre * op->Kp + 2 * d] = re;
+          a[(size_t)rre * op->Kp + 2 * d + 1] = -im;
+          a[(size_t)rim * op->Kp + 2 * d] = im;
+          a[(size_t)rim * op->Kp + 2 * d + 1] = re;
         }
       }
     } else {
       const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
-      op->Mp = (int)round_up(round_up(npair, 8), BM);
-      op->Kp = (int)round_up(npair, KSTEP) + KSTEP;
+      op->Mp = (int)round_up(round_up(np, 8), BM);
+      op->Kp = (int)round_up(np, KSTEP) + KSTEP;
       a.assign((size_t)op->Mp * op->Kp, 0.0);
-      for (int kl = 0; kl < npair; ++kl)
-        for (int ij = 0; ij < npair; ++ij)
-          a[(size_t)kl * op->Kp + ij] = h_h2p[2 * ((size_t)kl * npair + ij) + off];
+      for (int c = 0; c < np; ++c)
+        for (int d = 0; d < np; ++d) a[(size_t)c * op->Kp + d] = elem(c, d, off);
     }
     if (cudaMalloc(&op->d_A, sizeof(double) * a.size()) != cudaSuccess ||
         cudaMemcpy(op->d_A, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice) !=
@@ -355,6 +473,7 @@ extern "C" int fqeb_op_destroy(fqeb_op *op) {
   if (!op) return FQEB_OK;
   if (op->d_A) cudaFree(op->d_A);
   if (op->d_h1) cudaFree(op->d_h1);
+  if (op->d_pairs) cudaFree(op->d_pairs);
   free(op);
   return FQEB_OK;
 }
@@ -362,6 +481,13 @@ extern "C" int fqeb_op_destroy(fqeb_op *op) {
 extern "C" int fqeb_op_kind(const fqeb_op *op, int *kind) {
   FQEB_REQUIRE(op && kind, "fqeb_op_kind: NULL argument");
   *kind = op->kind;
+  return FQEB_OK;
+}
+
+extern "C" int fqeb_op_pair_space(const fqeb_op *op, int *npairs, int *symmetric) {
+  FQEB_REQUIRE(op, "fqeb_op_pair_space: NULL argument");
+  if (npairs) *npairs = op->np;
+  if (symmetric) *symmetric = op->sym ? 1 : 0;
   return FQEB_OK;
 }
 

@@ -38,14 +38,21 @@ __device__ __forceinline__ void axpy_sign(double2 &acc, int t, const double2 v) 
   }
 }
 
+// Pair list: D row c (c in [c0, c1)) is the sum of the excitation pairs
+// pairs[2c], pairs[2c+1] (second = -1 if absent).  The plain operator lists every
+// ij once; an operator that is symmetric under i<->j lists (ij, ji) so that the
+// compressed tensor D_c[i>=j] = D[ij] + D[ji] of the reference's real-integral
+// branch (fqe_data.py:2336-2353) is produced directly.
+//
 // WRITE_D: store D;  H1: accumulate sum_ij h1[ij]*D[ij] into sig (one-body term,
-// fqe_data.py:655 `einsum("ij,ijkl->kl", h1e, dvec)`).
+// fqe_data.py:655 `einsum("ij,ijkl->kl", h1e, dvec)`; h1 needs no symmetry).
 template <bool WRITE_D, bool H1>
 __global__ void __launch_bounds__(kTB)
 k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restrict__ amapT_a,
             const int32_t *__restrict__ amap_b, const double2 *__restrict__ coeff,
-            double2 *__restrict__ dvec, int64_t ldd, int64_t row0, int nbt, int ij0, int ij1,
-            const double2 *__restrict__ h1, double2 *__restrict__ sig) {
+            double2 *__restrict__ dvec, int64_t ldd, int64_t row0, int nbt, int c0, int c1,
+            const int32_t *__restrict__ pairs, const double2 *__restrict__ h1,
+            double2 *__restrict__ sig) {
   const int64_t tile = blockIdx.x;
   const int64_t r = tile / nbt;
   const int64_t b = (tile % nbt) * kTB + threadIdx.x;
@@ -55,19 +62,27 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
   const double2 *__restrict__ crow = coeff + a * lenb;
   double2 *__restrict__ dout = dvec + r * lenb + b;
   double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 4
-  for (int ij = ij0; ij < ij1; ++ij) {
-    const int ta = ta_row[ij];                         // warp-uniform
-    const int tb = amap_b[(int64_t)ij * lenb + b];     // coalesced
-    double2 val = make_double2(0.0, 0.0);
-    if (ta != 0) axpy_sign(val, ta, coeff[(int64_t)(abs(ta) - 1) * lenb + b]);
-    if (tb != 0) axpy_sign(val, tb, crow[abs(tb) - 1]);
-    if (WRITE_D) dout[(int64_t)(ij - ij0) * ldd] = val;
-    if (H1) {
-      const double2 h = h1[ij];
-      acc.x += h.x * val.x - h.y * val.y;
-      acc.y += h.x * val.y + h.y * val.x;
+#pragma unroll 2
+  for (int c = c0; c < c1; ++c) {
+    double2 tot = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ij = pairs[2 * c + h];  // warp-uniform
+      if (ij < 0) continue;
+      const int ta = ta_row[ij];                         // warp-uniform
+      const int tb = amap_b[(int64_t)ij * lenb + b];     // coalesced
+      double2 val = make_double2(0.0, 0.0);
+      if (ta != 0) axpy_sign(val, ta, coeff[(int64_t)(abs(ta) - 1) * lenb + b]);
+      if (tb != 0) axpy_sign(val, tb, crow[abs(tb) - 1]);
+      tot.x += val.x;
+      tot.y += val.y;
+      if (H1) {
+        const double2 hh = h1[ij];
+        acc.x += hh.x * val.x - hh.y * val.y;
+        acc.y += hh.x * val.y + hh.y * val.x;
+      }
     }
+    if (WRITE_D) dout[(int64_t)(c - c0) * ldd] = tot;
   }
   if (H1) {
     double2 s = sig[a * lenb + b];
@@ -79,8 +94,9 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
 
 __global__ void __launch_bounds__(kTB)
 k_make_coeff(int npair, int64_t lena, int64_t lenb, const int32_t *__restrict__ amapT_a,
-             const int32_t *__restrict__ amap_b, const double2 *__restrict__ evec, int64_t lde,
-             int64_t row0, int64_t nrows, int nbt, double2 z, double2 *__restrict__ out) {
+             const int32_t *__restrict__ amap_b, const int32_t *__restrict__ rowmap,
+             const double2 *__restrict__ evec, int64_t lde, int64_t row0, int64_t nrows, int nbt,
+             double2 z, double2 *__restrict__ out) {
   const int64_t tile = blockIdx.x;
   const int64_t x = tile / nbt;
   const int64_t b = (tile % nbt) * kTB + threadIdx.x;
@@ -96,7 +112,7 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, const int32_t *__restrict__ 
       const int64_t y = (int64_t)(abs(ta) - 1) - row0;
       if (y >= 0 && y < nrows) {
         touched = true;
-        axpy_sign(acc, ta, evec[(int64_t)kl * lde + y * lenb + b]);
+        axpy_sign(acc, ta, evec[(int64_t)rowmap[kl] * lde + y * lenb + b]);
       }
     }
   }
@@ -108,7 +124,7 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, const int32_t *__restrict__ 
 #pragma unroll 4
     for (int kl = 0; kl < npair; ++kl) {
       const int tb = amap_b[(int64_t)kl * lenb + b];
-      if (tb != 0) axpy_sign(acc, tb, erow[(int64_t)kl * lde + (abs(tb) - 1)]);
+      if (tb != 0) axpy_sign(acc, tb, erow[(int64_t)rowmap[kl] * lde + (abs(tb) - 1)]);
     }
   }
   if (touched) {
@@ -119,10 +135,13 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, const int32_t *__restrict__ 
   }
 }
 
+// pairs == nullptr: identity pair list of the graph (D row c <-> pair c), np_eff = norb^2
 int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
-                     int64_t row0, int64_t nrows, int ij0, int ij1, const double *d_h1,
-                     double *d_sig, cudaStream_t st) {
-  const int npair = g->norb * g->norb;
+                     int64_t row0, int64_t nrows, int ij0, int ij1, const int32_t *d_pairs,
+                     int np_eff, const double *d_h1, double *d_sig, cudaStream_t st) {
+  const int npair_full = g->norb * g->norb;
+  const int npair = d_pairs ? np_eff : npair_full;
+  if (!d_pairs) d_pairs = g->d_pairs_id;
   const int64_t lena = g->len[0], lenb = g->len[1];
   FQEB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= lena,
                "make_dvec: rows [%lld,+%lld) outside [0,%lld)", (long long)row0, (long long)nrows,
@@ -140,9 +159,9 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
   const double2 *h1 = (const double2 *)d_h1;
   double2 *sig = (double2 *)d_sig;
 #define FQEB_LAUNCH_DVEC(WD, HH)                                                              \
-  k_make_dvec<WD, HH><<<(unsigned)tiles, kTB, 0, st>>>(npair, lena, lenb, g->d_amapT[0],     \
-                                                       g->d_amap[1], c, d, ldd, row0, nbt,   \
-                                                       ij0, ij1, h1, sig)
+  k_make_dvec<WD, HH><<<(unsigned)tiles, kTB, 0, st>>>(npair_full, lena, lenb, g->d_amapT[0], \
+                                                       g->d_amap[1], c, d, ldd, row0, nbt,    \
+                                                       ij0, ij1, d_pairs, h1, sig)
   if (d && h1) FQEB_LAUNCH_DVEC(true, true);
   else if (d) FQEB_LAUNCH_DVEC(true, false);
   else if (h1) FQEB_LAUNCH_DVEC(false, true);
@@ -152,8 +171,11 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
   return FQEB_OK;
 }
 
+// rowmap == nullptr: identity (E row kl <-> pair kl)
 int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t row0,
-                      int64_t nrows, double zr, double zi, double *d_out, cudaStream_t st) {
+                      int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
+                      double *d_out, cudaStream_t st) {
+  if (!d_rowmap) d_rowmap = g->d_rowmap_id;
   const int npair = g->norb * g->norb;
   const int64_t lena = g->len[0], lenb = g->len[1];
   FQEB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= lena,
@@ -165,8 +187,9 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
   const int64_t tiles = lena * nbt;
   FQEB_REQUIRE(tiles < (1ll << 31), "make_coeff: problem too large for one launch");
   k_make_coeff<<<(unsigned)tiles, kTB, 0, st>>>(npair, lena, lenb, g->d_amapT[0], g->d_amap[1],
-                                                (const double2 *)d_evec, lde, row0, nrows, nbt,
-                                                make_double2(zr, zi), (double2 *)d_out);
+                                                d_rowmap, (const double2 *)d_evec, lde, row0,
+                                                nrows, nbt, make_double2(zr, zi),
+                                                (double2 *)d_out);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }
@@ -179,8 +202,8 @@ extern "C" int fqeb_make_dvec(const fqeb_graph *g, const double *d_coeff, double
   int rc = fqeb::require_device();
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(g && d_coeff && d_dvec, "fqeb_make_dvec: NULL argument");
-  return fqeb::launch_make_dvec(g, d_coeff, d_dvec, ldd, row0, nrows, ij0, ij1, nullptr, nullptr,
-                                (cudaStream_t)stream);
+  return fqeb::launch_make_dvec(g, d_coeff, d_dvec, ldd, row0, nrows, ij0, ij1, nullptr, 0,
+                                nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int fqeb_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde,
@@ -189,6 +212,6 @@ extern "C" int fqeb_make_coeff(const fqeb_graph *g, const double *d_evec, int64_
   int rc = fqeb::require_device();
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(g && d_evec && d_out, "fqeb_make_coeff: NULL argument");
-  return fqeb::launch_make_coeff(g, d_evec, lde, row0, nrows, zr, zi, d_out,
+  return fqeb::launch_make_coeff(g, d_evec, lde, row0, nrows, nullptr, zr, zi, d_out,
                                  (cudaStream_t)stream);
 }

@@ -68,6 +68,8 @@ struct fqeb_graph {
   double *d_small;         // scratch for small operator uploads (diag, v, ...)
   size_t small_bytes;
   double *d_sterm[2];      // per-string diagonal-Coulomb terms, complex [len]
+  int32_t *d_pairs_id;     // identity pair list [norb^2][2] = (ij, -1)
+  int32_t *d_rowmap_id;    // identity row map [norb^2]
 };
 
 struct fqeb_op {
@@ -75,9 +77,14 @@ struct fqeb_op {
   int kind;           // FQEB_OP_*
   bool has_h2;
   int device;
+  bool sym;           // h2'[ij,kl] symmetric under i<->j and k<->l: pairs compressed to i>=j
+  int np;             // size of the pair space the contraction runs over:
+                      //   norb^2, or norb(norb+1)/2 when sym
+  int32_t *d_pairs;   // [np][2] excitation pairs summed into D row c (second -1 if none)
+  int32_t *d_rowmap;  // [norb^2] E row holding pair kl
   // GEMM operand: real row-major [Mp][Kp]; layout depends on kind (see dgemm.cu)
   double *d_A;
-  int Mp, Kp;         // padded real dims of the FULL operator (all ij)
+  int Mp, Kp;         // padded real dims of the FULL operator (whole pair space)
   double *d_h1;       // complex [norb*norb] (h1' / z), interleaved
   double zr, zi;      // global factor: 1 (real/complex) or i (imag)
 };

@@ -207,6 +207,22 @@ extern "C" int fqeb_graph_create(int norb, int nalpha, int nbeta, fqeb_graph **o
     set_error("fqeb_graph_create: scratch allocation failed");
     return fail(FQEB_ERR_CUDA);
   }
+  {
+    const int npair = norb * norb;
+    std::vector<int32_t> ids(3 * (size_t)(npair > 0 ? npair : 1));
+    for (int p = 0; p < npair; ++p) {
+      ids[2 * p] = p;
+      ids[2 * p + 1] = -1;
+      ids[2 * npair + p] = p;
+    }
+    if (cudaMalloc(&g->d_pairs_id, sizeof(int32_t) * ids.size()) != cudaSuccess ||
+        cudaMemcpy(g->d_pairs_id, ids.data(), sizeof(int32_t) * ids.size(),
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("fqeb_graph_create: pair table allocation failed");
+      return fail(FQEB_ERR_CUDA);
+    }
+    g->d_rowmap_id = g->d_pairs_id + 2 * npair;
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("fqeb_graph_create: table kernels failed: %s",
               cudaGetErrorString(cudaGetLastError()));
@@ -228,6 +244,7 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
   }
   for (int s = 0; s < 2; ++s) free(g->h_Z[s]);
   if (g->d_small) cudaFree(g->d_small);
+  if (g->d_pairs_id) cudaFree(g->d_pairs_id);
   for (int s = 0; s < 2; ++s)
     if (g->d_sterm[s]) cudaFree(g->d_sterm[s]);
   free(g);

@@ -24,13 +24,15 @@
 
 namespace fqeb {
 int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
-                     int64_t row0, int64_t nrows, int ij0, int ij1, const double *d_h1,
-                     double *d_sig, cudaStream_t st);
+                     int64_t row0, int64_t nrows, int ij0, int ij1, const int32_t *d_pairs,
+                     int np_eff, const double *d_h1, double *d_sig, cudaStream_t st);
 int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t row0,
-                      int64_t nrows, double zr, double zi, double *d_out, cudaStream_t st);
+                      int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
+                      double *d_out, cudaStream_t st);
 int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
                     int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st);
 int dvec_rows_padded(const fqeb_op *op, int nij);
+int dvec_rows_zeroed(const fqeb_op *op, int nij);
 
 // ---- optional per-phase event timing ------------------------------------------------
 struct PhaseEvent {
@@ -72,10 +74,9 @@ struct ChunkLayout {
 static ChunkLayout layout_for(const fqeb_graph *g, const fqeb_op *op, int64_t rows, int ij0,
                               int ij1) {
   ChunkLayout L;
-  const int npair = g->norb * g->norb;
   L.ldd = round_up(rows * g->len[1], fqeb_gemm_col_align());
   L.d_rows = dvec_rows_padded(op, ij1 - ij0);
-  L.e_rows = round_up(npair, 8);
+  L.e_rows = round_up(op->np, 8);
   L.d_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.d_rows * L.ldd, 256);
   L.e_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.e_rows * L.ldd, 256);
   return L;
@@ -89,9 +90,9 @@ static int check_shard(const fqeb_graph *g, const fqeb_op *op, int ij0, int ij1)
   FQEB_REQUIRE(g && op, "sigma: NULL handle");
   FQEB_REQUIRE(op->norb == g->norb, "sigma: operator has %d orbitals, graph has %d", op->norb,
                g->norb);
-  const int npair = g->norb * g->norb;
-  FQEB_REQUIRE(ij0 >= 0 && ij0 <= ij1 && ij1 <= npair, "sigma: pair slice [%d,%d) invalid", ij0,
-               ij1);
+  FQEB_REQUIRE(ij0 >= 0 && ij0 <= ij1 && ij1 <= op->np,
+               "sigma: pair slice [%d,%d) outside the operator's pair space [0,%d)", ij0, ij1,
+               op->np);
   return FQEB_OK;
 }
 
@@ -134,8 +135,8 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
 
   if (!op->has_h2) {
     // one-body operator: sigma = sum_ij h1[ij] D[ij], D never materialised
-    return launch_make_dvec(g, d_coeff, nullptr, 0, row0, row1 - row0, ij0, ij1, op->d_h1, d_sigma,
-                            st);
+    return launch_make_dvec(g, d_coeff, nullptr, 0, row0, row1 - row0, ij0, ij1, op->d_pairs,
+                            op->np, op->d_h1, d_sigma, st);
   }
   FQEB_REQUIRE((ij0 & 1) == 0, "sigma: pair slice must start at an even index");
   const int64_t rows_max = fqeb_sigma_rows_for_workspace(g, op, workspace_bytes, ij0, ij1);
@@ -152,16 +153,19 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   double *d_dvec = (double *)d_workspace;
   double *d_evec = (double *)((char *)d_workspace + L.d_bytes);
   const int nij = ij1 - ij0;
-  if (L.d_rows > nij) {
-    // k-padding rows of D must be exact zeros (they meet finite operator entries)
+  const int zrows = dvec_rows_zeroed(op, nij);
+  if (zrows > nij) {
+    // the k-padding rows of D that a partial k4 step reads must be exact zeros
+    // (they meet finite operator entries)
     FQEB_CUDA(cudaMemsetAsync(d_dvec + 2 * (size_t)nij * L.ldd, 0,
-                              sizeof(double) * 2 * (size_t)(L.d_rows - nij) * L.ldd, st));
+                              sizeof(double) * 2 * (size_t)(zrows - nij) * L.ldd, st));
   }
   for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
     const int64_t nr = (row1 - a0) < rows_chunk ? (row1 - a0) : rows_chunk;
     {
       PhaseTimer t(0, st);
-      rc = launch_make_dvec(g, d_coeff, d_dvec, L.ldd, a0, nr, ij0, ij1, op->d_h1, d_sigma, st);
+      rc = launch_make_dvec(g, d_coeff, d_dvec, L.ldd, a0, nr, ij0, ij1, op->d_pairs, op->np,
+                            op->d_h1, d_sigma, st);
     }
     if (rc != FQEB_OK) return rc;
     {
@@ -171,7 +175,8 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
     if (rc != FQEB_OK) return rc;
     {
       PhaseTimer t(2, st);
-      rc = launch_make_coeff(g, d_evec, L.ldd, a0, nr, op->zr, op->zi, d_sigma, st);
+      rc = launch_make_coeff(g, d_evec, L.ldd, a0, nr, op->d_rowmap, op->zr, op->zi, d_sigma,
+                             st);
     }
     if (rc != FQEB_OK) return rc;
   }
@@ -248,7 +253,7 @@ extern "C" int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta, const
     if (d_ws) cudaFree(d_ws);
     fqeb_op_destroy(op);
   };
-  const int npair = norb * norb;
+  const int npair = op->np;
   if (cudaMalloc(&d_c, cbytes) != cudaSuccess || cudaMalloc(&d_s, cbytes) != cudaSuccess) {
     set_error("sigma_host: cannot allocate coefficient buffers (%zu bytes each)", cbytes);
     cleanup();

@@ -38,9 +38,9 @@ def split_even(total: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
     return out
 
 
-def shard_plan(mode: str, rank: int, world: int, lena: int, norb: int):
-    """(row_range, pair_range) of one rank."""
-    npair = norb * norb
+def shard_plan(mode: str, rank: int, world: int, lena: int, npair: int):
+    """(row_range, pair_range) of one rank; ``npair`` is the size of the operator's pair
+    space (``DenseOperator.npair``: norb^2, or norb(norb+1)/2 when compressed)."""
     if mode == "det":
         return split_even(lena, world)[rank], (0, npair)
     if mode == "pair":
@@ -63,6 +63,6 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return sector.apply_operator(op)
     rows, pairs = shard_plan(mode, dist.get_rank(), dist.get_world_size(), sector.lena(),
-                             sector.norb())
+                             op.npair)
     part = sector.apply_operator(op, row_range=rows, pair_range=pairs)
     return allreduce_sigma(part)

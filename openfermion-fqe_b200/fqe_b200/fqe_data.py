@@ -140,6 +140,10 @@ class DenseOperator:
         kind = ctypes.c_int()
         _lib.call("fqeb_op_kind", handle, ctypes.byref(kind))
         self.kind = int(kind.value)
+        npairs, sym = ctypes.c_int(), ctypes.c_int()
+        _lib.call("fqeb_op_pair_space", handle, ctypes.byref(npairs), ctypes.byref(sym))
+        self.npair = int(npairs.value)      # pair space of the contraction
+        self.symmetric = bool(sym.value)    # i>=j compressed (real-orbital integrals)
 
     @property
     def handle(self) -> ctypes.c_void_p:
@@ -364,9 +368,8 @@ class FqeData:
         dev = _require_cuda()
         if op.norb != self.norb():
             raise ValueError("operator / wavefunction orbital mismatch")
-        npair = self.norb() * self.norb()
         r0, r1 = row_range if row_range is not None else (0, self.lena())
-        p0, p1 = pair_range if pair_range is not None else (0, npair)
+        p0, p1 = pair_range if pair_range is not None else (0, op.npair)
         sigma = torch.empty_like(self.coeff)
         ws_ptr, ws_bytes = None, 0
         if op.has_h2 and r1 > r0 and p1 > p0:

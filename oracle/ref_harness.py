@@ -44,6 +44,7 @@ _LIB_PATH = _pick_lib_path()
 
 _lib = None
 _blas = None
+_blas_limit = None
 
 
 def available() -> bool:
@@ -58,6 +59,15 @@ def lib():
                 f"{_LIB_PATH} missing: run `make -C oracle` where /root/reference exists")
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.fqe_oracle_blas.restype = c_void_p
+        # The reference calls BLAS zaxpy from inside its own OpenMP loops; scipy's
+        # OpenBLAS must not spawn threads of its own there (it warns and can
+        # oversubscribe for vectors > ~10^4), so pin BLAS to one thread per caller.
+        try:
+            from threadpoolctl import threadpool_limits
+            global _blas_limit
+            _blas_limit = threadpool_limits(limits=1, user_api="blas")
+        except Exception:  # pragma: no cover
+            pass
     return _lib
 
 

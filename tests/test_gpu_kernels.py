@@ -134,6 +134,55 @@ def test_contract_matches_matmul(norb, kind):
         assert torch.all(ev[npair:] == 5.0)  # rows beyond norb^2 untouched
 
 
+def test_contract_pair_symmetric_operator():
+    """h2'[ij,kl] symmetric under i<->j, k<->l -> contraction in the i>=j pair space"""
+    from fqe_b200 import lib as L
+    from fqe_b200.fqe_data import DenseOperator
+    for norb, cplx in [(3, False), (6, True), (8, False), (16, False), (16, True)]:
+        rng = np.random.default_rng(norb + 5)
+        w = _rand_c(rng, (norb,) * 4) if cplx else rng.standard_normal((norb,) * 4) + 0j
+        h2p4 = w + w.transpose(1, 0, 2, 3)
+        h2p4 = h2p4 + h2p4.transpose(0, 1, 3, 2)
+        op = DenseOperator(norb, np.zeros((norb, norb)), -np.moveaxis(h2p4, 2, 1))
+        npc = norb * (norb + 1) // 2
+        assert op.symmetric and op.npair == npc
+        assert op.kind == (L.OP_COMPLEX if cplx else L.OP_REAL)
+        pairs = [(i, j) for i in range(norb) for j in range(i + 1)]
+        h2c = np.array([[h2p4[i, j, k, l] for (k, l) in pairs] for (i, j) in pairs])
+        lib = L.load()
+        ncols = 200
+        ld = 256
+        drows = lib.fqeb_contract_dvec_rows(op.handle, npc)
+        dv = torch.zeros((drows, ld), dtype=torch.complex128, device="cuda")
+        dhost = _rand_c(rng, (npc, ncols))
+        dv[:npc, :ncols] = torch.from_numpy(dhost).cuda()
+        ev = torch.zeros((npc + 8, ld), dtype=torch.complex128, device="cuda")
+        L.call("fqeb_contract", op.handle, dv.data_ptr(), ld, ev.data_ptr(), ld, ncols, 0, npc,
+               None)
+        torch.cuda.synchronize()
+        assert O.rel_err(ev[:npc, :ncols].cpu().numpy(), h2c @ dhost) < TOL
+
+
+def test_symmetry_switch(monkeypatch):
+    """FQEB_NO_SYMMETRY disables the compression; both routes give the same sigma"""
+    from fqe_b200 import synth
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    na, nb, norb = 3, 4, 7
+    h1, h2 = synth.integrals(norb, "real8")
+    d, c, _ = _data(na, nb, norb)
+    op_sym = DenseOperator(norb, h1, h2)
+    assert op_sym.symmetric and op_sym.npair == 28
+    op_t = DenseOperator(norb, -0.1j * h1, -0.1j * h2)   # Taylor's iht tensors
+    assert op_t.symmetric and op_t.kind == 1
+    monkeypatch.setenv("FQEB_NO_SYMMETRY", "1")
+    op_full = DenseOperator(norb, h1, h2)
+    assert (not op_full.symmetric) and op_full.npair == 49
+    ref = O.sigma_restricted(O.graph(na, nb, norb), c, h1, h2)
+    assert O.rel_err(d.apply_operator(op_sym).cpu().numpy(), ref) < TOL
+    assert O.rel_err(d.apply_operator(op_full).cpu().numpy(), ref) < TOL
+    assert O.rel_err(d.apply_operator(op_t).cpu().numpy(), -0.1j * ref) < TOL
+
+
 DC_CFGS = [(2, 3, 6), (2, 1, 4), (4, 4, 8), (0, 2, 4), (3, 3, 3), (5, 4, 9)]
 
 

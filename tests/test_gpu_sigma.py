@@ -101,7 +101,7 @@ def test_sigma_chunked_and_sharded():
         d.set_wfn(strategy="from_data", raw_data=c)
         op = DenseOperator(norb, h1, h2)
         lib = L.load()
-        npair = norb * norb
+        npair = op.npair
         la = d.lena()
 
         def run(rows_per_chunk, r0, r1, p0, p1):
@@ -120,7 +120,11 @@ def test_sigma_chunked_and_sharded():
         parts = [run(7, r0, r1, 0, npair) for r0, r1 in [(0, 20), (20, 50), (50, la)]]
         assert O.rel_err(sum(parts), ref) < TOL
         # pair (ij) shards as in north_star (world of 4)
-        parts = [run(11, 0, la, p0, p1) for p0, p1 in [(0, 16), (16, 32), (32, 48), (48, 64)]]
+        from fqe_b200.distributed import shard_plan
+        parts = [run(11, *shard_plan("pair", r, 4, la, npair)[0], *shard_plan("pair", r, 4, la, npair)[1])
+                 for r in range(4)]
+        assert O.rel_err(sum(parts), ref) < TOL
+        parts = [run(11, 0, la, p0, p1) for p0, p1 in [(0, 6), (6, 20), (20, npair)]]
         assert O.rel_err(sum(parts), ref) < TOL
         # too-small workspace is an error, not a crash
         out = torch.empty_like(d.coeff)
