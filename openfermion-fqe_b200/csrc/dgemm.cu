@@ -25,9 +25,11 @@
 //             8 imaginary-part rows of the same kl) so that each thread ends up
 //             holding (re, im) of the same output element and the epilogue writes
 //             interleaved complex128 with 16-byte stores.
-//   * CTA tile 128 (real rows) x 128 (real cols / dets), 8 warps as 2(M) x 4(N),
-//     warp tile 64x32 = 8x4 DMMA tiles, 64 FP64 accumulators per thread,
-//     4-stage cp.async pipeline (146 KB shared memory), k-step 16.
+//   * CTA tile BM (real rows) x 128 (real cols), 8 warps, 4-stage cp.async pipeline,
+//     k-step 16.  "wide" shape: 128 x 128, warps 2(M) x 4(N), warp tile 8x4 DMMA tiles
+//     (64 accumulators per thread, 146 KB smem).  "tall" shapes: 8w x 128 with every
+//     warp spanning all rows (w x 2 DMMA tiles), w picked from a small menu so that
+//     the operator's row count is covered without a ragged block.
 //   * shared-memory strides (20 / 132 / 264 doubles) make every fragment load
 //     bank-conflict free for 64-bit accesses.
 //   * persistent grid (one CTA per SM) with the pipeline running across tile
@@ -43,19 +45,16 @@
 
 namespace fqeb {
 
-constexpr int BM = 128;       // real rows per CTA
-constexpr int BNR = 128;      // real columns per CTA
+constexpr int BNR = 128;      // real columns per CTA tile
 constexpr int KSTEP = 16;     // real k per pipeline stage
 constexpr int STAGES = 4;
 constexpr int A_STRIDE = KSTEP + 4;   // doubles
 constexpr int B_STRIDE_R = BNR + 4;   // REAL: [16][132]
 constexpr int B_STRIDE_C = 2 * BNR + 8;  // CPLX: [8][264]
-constexpr int A_TILE = BM * A_STRIDE;            // doubles
 constexpr int B_TILE = 16 * B_STRIDE_R;          // == 8 * B_STRIDE_C
 static_assert(16 * B_STRIDE_R == 8 * B_STRIDE_C, "B tile size mismatch");
-constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
-constexpr size_t GEMM_SMEM = sizeof(double) * STAGE_DOUBLES * STAGES;
 constexpr int COL_ALIGN = 128;  // leading dimensions (complex elements) must be multiples
+constexpr int MAX_BM = 144;     // tallest CTA tile of the menu below (operand row padding)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -74,59 +73,71 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// CTA tile = BM x 128 real elements, 8 warps arranged WARPS_M x (8/WARPS_M); each
+// warp owns WM x WN DMMA (8x8) tiles.  Two shapes are instantiated:
+//   wide  WARPS_M=2, WM=8, WN=4 : 128 x 128, for row counts that are multiples of 128
+//   tall  WARPS_M=1, WM=w, WN=2 : 8w x 128, every warp spans all rows; w is chosen so
+//         that the operator's row count is covered without a ragged last block
+//         (e.g. the 136 compressed pairs of norb=16 -> w=17, one block).
+//
 // A: real row-major, leading dimension lda (doubles); a_col0 = first real k of the slice.
 // B: complex [.][ldb] (D rows of the slice start at row 0).  E: complex [.][lde].
 // m_valid: real rows of A that carry data (multiple of 8; of 16 for CPLX).
 // k_valid: real k extent of the slice (the last stage may be partial: only whole k4
-//          steps that contain data are issued; D rows / A columns beyond it are zero
-//          or meet zeros).  nrows_out: valid complex output rows.
+//          steps that contain data are issued).  nrows_out: valid complex output rows.
 //
-// PERSISTENT: the grid is one CTA per SM; CTA c walks tiles c, c+grid, ... (M-fastest
-// order, so the CTAs that share a D tile run at the same time) and the cp.async
-// pipeline runs CONTINUOUSLY across tile boundaries: while the last stages of a tile
-// are in the tensor cores the first stages of the next tile are already in flight,
-// and the epilogue's stores overlap those loads.  This removes the per-tile
-// fill/drain bubble that a one-tile-per-CTA launch pays (~10% at K=256).
-template <bool CPLX>
+// The kernel is grid-strided over tiles (M-fastest order, so the CTAs that share a D
+// tile run at the same time) and the cp.async pipeline runs CONTINUOUSLY across tile
+// boundaries: launched with one CTA per SM it is persistent - the first stages of
+// the next tile are in flight while the last stages of the current one are in the
+// tensor cores and the epilogue's stores overlap those loads; launched with one CTA
+// per tile it degenerates to the classic kernel.
+template <bool CPLX, int WARPS_M, int WM, int WN>
 __global__ void __launch_bounds__(256, 1)
 k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
         int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out, int k_valid,
         int nmb, int64_t ntiles) {
+  constexpr int BM = WARPS_M * WM * 8;
+  constexpr int WARPS_N = 8 / WARPS_M;
+  static_assert(WARPS_N * WN * 8 == BNR, "warp layout must span 128 columns");
+  static_assert(!CPLX || (WM % 2 == 0), "complex mode pairs re/im row tiles");
+  constexpr int A_TILE = BM * A_STRIDE;
+  constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
+  constexpr int TILE_DETS = CPLX ? BNR : BNR / 2;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
-  const int wm0 = (warp >> 2) * 64;
-  const int wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / WARPS_N) * (WM * 8);
+  const int wn0 = (warp % WARPS_N) * (WN * 8);
   const int nk = (k_valid + KSTEP - 1) / KSTEP;
-  constexpr int TILE_DETS = CPLX ? BNR : BNR / 2;
 
   if ((int64_t)blockIdx.x >= ntiles) return;
   const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int64_t total_it = my_tiles * nk;
 
-  double acc[8][4][2];
+  double acc[WM][WN][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // ---- producer state: (tile, kt) of the next stage to load --------------------------
   int64_t ld_tile = blockIdx.x;
   int ld_kt = 0;
-  auto issue_load = [&](int stage) {
-    const int mb = (int)(ld_tile % nmb);
-    const int64_t nb = ld_tile / nmb;
-    const double *Ag = A + (int64_t)(mb * BM) * lda + a_col0;
-    const double2 *Bg = B + nb * TILE_DETS;
-    double *As = smem + stage * STAGE_DOUBLES;
+  const double *ld_A = A + (int64_t)((int)(ld_tile % nmb) * BM) * lda + a_col0;
+  const double2 *ld_B = B + (ld_tile / nmb) * TILE_DETS;
+  int ld_stage = 0;
+  auto issue_load = [&]() {
+    double *As = smem + ld_stage * STAGE_DOUBLES;
     double *Bs = As + A_TILE;
     const int k0 = ld_kt * KSTEP;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < (BM * 8 + 255) / 256; ++i) {
       const int c = tid + i * 256;
       const int row = c >> 3, cc = c & 7;
-      cp_async16(As + row * A_STRIDE + cc * 2, Ag + (int64_t)row * lda + k0 + cc * 2);
+      if ((BM * 8) % 256 == 0 || row < BM)
+        cp_async16(As + row * A_STRIDE + cc * 2, ld_A + (int64_t)row * lda + k0 + cc * 2);
     }
     if (CPLX) {
       const int r0 = k0 >> 1;  // 8 complex rows of D per stage
@@ -134,54 +145,55 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
       for (int i = 0; i < 4; ++i) {
         const int c = tid + i * 256;
         const int row = c >> 7, cc = c & 127;
-        cp_async16(Bs + row * B_STRIDE_C + cc * 2, Bg + (int64_t)(r0 + row) * ldb + cc);
+        cp_async16(Bs + row * B_STRIDE_C + cc * 2, ld_B + (int64_t)(r0 + row) * ldb + cc);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = tid + i * 256;
         const int row = c >> 6, cc = c & 63;
-        cp_async16(Bs + row * B_STRIDE_R + cc * 2, Bg + (int64_t)(k0 + row) * ldb + cc);
+        cp_async16(Bs + row * B_STRIDE_R + cc * 2, ld_B + (int64_t)(k0 + row) * ldb + cc);
       }
     }
+    ld_stage = (ld_stage + 1 == STAGES) ? 0 : ld_stage + 1;
     if (++ld_kt == nk) {
       ld_kt = 0;
       ld_tile += gridDim.x;
+      ld_A = A + (int64_t)((int)(ld_tile % nmb) * BM) * lda + a_col0;
+      ld_B = B + (ld_tile / nmb) * TILE_DETS;
     }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < total_it) issue_load(s);
+    if (s < total_it) issue_load();
     cp_async_commit();
   }
 
   // ---- consumer state ------------------------------------------------------------------
   int64_t tile = blockIdx.x;
-  int kt = 0;
+  int kt = 0, stage = 0;
   int m0 = (int)(tile % nmb) * BM;
   int mt_active = (m_valid - (m0 + wm0)) / 8;
-  mt_active = mt_active < 0 ? 0 : (mt_active > 8 ? 8 : mt_active);
+  mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
 
   for (int64_t it = 0; it < total_it; ++it) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int64_t nxt = it + STAGES - 1;
-      if (nxt < total_it) issue_load((int)(nxt % STAGES));
-      cp_async_commit();
-    }
-    const double *As = smem + (int)(it % STAGES) * STAGE_DOUBLES;
+    if (it + STAGES - 1 < total_it) issue_load();
+    cp_async_commit();
+    const double *As = smem + stage * STAGE_DOUBLES;
     const double *Bs = As + A_TILE;
+    stage = (stage + 1 == STAGES) ? 0 : stage + 1;
     // whole k4 steps of this stage that contain data
     int kk_count = (k_valid - kt * KSTEP + 3) / 4;
     kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
 #pragma unroll
     for (int kk = 0; kk < KSTEP / 4; ++kk) {
       if (kk < kk_count) {
-        double bf[4];
+        double bf[WN];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < WN; ++nt) {
           const int n = wn0 + nt * 8 + g;
           if (CPLX) {
             bf[nt] = Bs[(kk * 2 + (tg >> 1)) * B_STRIDE_C + n * 2 + (tg & 1)];
@@ -190,11 +202,11 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
           }
         }
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < WM; ++mt) {
           if (mt < mt_active) {
             const double af = As[(wm0 + mt * 8 + g) * A_STRIDE + kk * 4 + tg];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
+            for (int nt = 0; nt < WN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
           }
         }
       }
@@ -205,13 +217,13 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
       const int64_t n0 = (tile / nmb) * TILE_DETS;
       if (CPLX) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < WM / 2; ++p) {
           if (2 * p < mt_active) {
             const int kl = ((m0 + wm0) >> 1) + p * 8 + g;
             if (kl < nrows_out) {
               double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt) {
+              for (int nt = 0; nt < WN; ++nt) {
                 erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
                 erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
               }
@@ -220,33 +232,90 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
         }
       } else {
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < WM; ++mt) {
           if (mt < mt_active) {
             const int kl = m0 + wm0 + mt * 8 + g;
             if (kl < nrows_out) {
               double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
-              for (int nt = 0; nt < 4; ++nt)
+              for (int nt = 0; nt < WN; ++nt)
                 erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             }
           }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       kt = 0;
       tile += gridDim.x;
       m0 = (int)(tile % nmb) * BM;
       mt_active = (m_valid - (m0 + wm0)) / 8;
-      mt_active = mt_active < 0 ? 0 : (mt_active > 8 ? 8 : mt_active);
+      mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
     }
   }
   cp_async_wait<0>();
 }
 
-static bool g_attr_set[2] = {false, false};
+// ---- tile-shape menu ---------------------------------------------------------------
+struct GemmShape {
+  int warps_m, wm;
+  int bm() const { return warps_m * wm * 8; }
+};
+static const GemmShape kShapes[] = {{2, 8}, {1, 18}, {1, 17}, {1, 14}, {1, 13}, {1, 10}};
+
+template <bool CPLX, int WARPS_M, int WM, int WN>
+static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int64_t ldd,
+                        double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
+                        cudaStream_t st) {
+  constexpr int BM = WARPS_M * WM * 8;
+  constexpr size_t SMEM = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES;
+  static bool attr_set = false;
+  auto kern = k_dgemm<CPLX, WARPS_M, WM, WN>;
+  if (!attr_set) {
+    FQEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  const int nmb = (m_valid + BM - 1) / BM;
+  const int64_t tiles = nnb * nmb;
+  // persistent: one CTA per SM, rounded down to a multiple of nmb so that the CTAs
+  // sharing a D tile stay aligned.  FQEB_GEMM_PERSISTENT=0 launches one CTA per tile.
+  static const bool persistent = !(getenv("FQEB_GEMM_PERSISTENT") &&
+                                   getenv("FQEB_GEMM_PERSISTENT")[0] == '0');
+  int64_t grid = tiles;
+  if (persistent) {
+    grid = sm_count();
+    if (grid > nmb) grid -= grid % nmb;
+    if (grid > tiles) grid = tiles;
+  }
+  FQEB_REQUIRE(grid < (1ll << 31), "contract: too many tiles for one launch");
+  kern<<<(unsigned)grid, 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+                                          (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
+                                          tiles);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
+// rows covered per block and the resulting padded row count for a shape
+static int padded_rows(const GemmShape &s, int m_valid) {
+  const int bm = s.bm();
+  return (m_valid + bm - 1) / bm * bm;
+}
+
+static GemmShape pick_shape(bool cplx, int m_valid) {
+  GemmShape best = kShapes[0];
+  int best_rows = padded_rows(best, m_valid);
+  for (const GemmShape &s : kShapes) {
+    if (cplx && (s.wm & 1)) continue;
+    const int rows = padded_rows(s, m_valid);
+    if (rows < best_rows) {
+      best = s;
+      best_rows = rows;
+    }
+  }
+  return best;
+}
 
 int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
                     int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st) {
@@ -266,37 +335,32 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
   const int a_col0 = cplx ? 2 * ij0 : ij0;
   FQEB_REQUIRE(a_col0 + nk * KSTEP <= op->Kp, "contract: operator padding too small");
   const int m_valid = cplx ? 2 * (int)round_up(np, 8) : (int)round_up(np, 8);
-  const int nmb = (m_valid + BM - 1) / BM;
   const int64_t cols_pad = round_up(ncols, COL_ALIGN);
   const int64_t nnb = cols_pad / (cplx ? BNR : BNR / 2);
-  const int64_t tiles = nnb * nmb;
-  const int idx = cplx ? 1 : 0;
-  if (!g_attr_set[idx]) {
-    if (cplx) {
-      FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)GEMM_SMEM));
-    } else {
-      FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)GEMM_SMEM));
-    }
-    g_attr_set[idx] = true;
+  const GemmShape sh = pick_shape(cplx, m_valid);
+  FQEB_REQUIRE(padded_rows(sh, m_valid) <= op->Mp, "contract: operator row padding too small");
+#define FQEB_SHAPE_BOTH(WMV, WARPSM, WNV)                                                      \
+  if (sh.warps_m == WARPSM && sh.wm == WMV) {                                                  \
+    return cplx ? launch_shape<true, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,   \
+                                                       m_valid, k_valid, nnb, st)              \
+                : launch_shape<false, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,  \
+                                                        m_valid, k_valid, nnb, st);            \
   }
-  // persistent: one CTA per SM, rounded down to a multiple of nmb so that the CTAs
-  // sharing a D tile stay aligned
-  int64_t grid = sm_count();
-  if (grid > nmb) grid -= grid % nmb;
-  if (grid > tiles) grid = tiles;
-  if (cplx) {
-    k_dgemm<true><<<(unsigned)grid, 256, GEMM_SMEM, st>>>(
-        op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd, (double2 *)d_evec, lde, m_valid,
-        np, k_valid, nmb, tiles);
-  } else {
-    k_dgemm<false><<<(unsigned)grid, 256, GEMM_SMEM, st>>>(
-        op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd, (double2 *)d_evec, lde, m_valid,
-        np, k_valid, nmb, tiles);
+#define FQEB_SHAPE_REAL(WMV, WARPSM, WNV)                                                      \
+  if (!cplx && sh.warps_m == WARPSM && sh.wm == WMV) {                                         \
+    return launch_shape<false, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,         \
+                                                 m_valid, k_valid, nnb, st);                   \
   }
-  FQEB_CHECK_LAUNCH();
-  return FQEB_OK;
+  FQEB_SHAPE_BOTH(8, 2, 4)
+  FQEB_SHAPE_BOTH(18, 1, 2)
+  FQEB_SHAPE_REAL(17, 1, 2)
+  FQEB_SHAPE_BOTH(14, 1, 2)
+  FQEB_SHAPE_REAL(13, 1, 2)
+  FQEB_SHAPE_BOTH(10, 1, 2)
+#undef FQEB_SHAPE_BOTH
+#undef FQEB_SHAPE_REAL
+  set_error("contract: no kernel instantiated for tile shape %dx%d", sh.warps_m, sh.wm);
+  return FQEB_ERR_INVALID;
 }
 
 // rows of D a caller must allocate for a slice of nij pairs (whole pipeline stages) ...
@@ -436,7 +500,7 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
     std::vector<double> a;
     if (op->kind == FQEB_OP_COMPLEX) {
       const int np8 = (int)round_up(np, 8);
-      op->Mp = (int)round_up(2 * np8, BM);
+      op->Mp = (int)round_up(2 * np8, MAX_BM) + MAX_BM;
       op->Kp = (int)round_up(2 * np, KSTEP) + KSTEP;  // slack for ragged slices
       a.assign((size_t)op->Mp * op->Kp, 0.0);
       for (int c = 0; c < np; ++c) {
@@ -451,7 +515,7 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
       }
     } else {
       const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
-      op->Mp = (int)round_up(round_up(np, 8), BM);
+      op->Mp = (int)round_up(round_up(np, 8), MAX_BM) + MAX_BM;
       op->Kp = (int)round_up(np, KSTEP) + KSTEP;
       a.assign((size_t)op->Mp * op->Kp, 0.0);
       for (int c = 0; c < np; ++c)
