@@ -122,45 +122,60 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
 #pragma unroll
     for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // ---- producer state: (tile, kt) of the next stage to load --------------------------
-  int64_t ld_tile = blockIdx.x;
-  int ld_kt = 0;
-  const double *ld_A = A + (int64_t)((int)(ld_tile % nmb) * BM) * lda + a_col0;
-  const double2 *ld_B = B + (ld_tile / nmb) * TILE_DETS;
-  int ld_stage = 0;
+  // tile walk without divisions: tile -> (mb, nb), advanced by (mb_step, nb_step)
+  const int mb_step = (int)(gridDim.x % nmb);
+  const int64_t nb_step = gridDim.x / nmb;
+
+  // ---- producer: per-thread source/destination of its cp.async slots -----------------
+  // slot i of A covers rows i*32 + tid/8 (8 x 16-byte chunks per row); slot i of B covers
+  // rows i*B_ROWS + tid/B_CHUNKS.  Only one pointer per operand is thread-dependent.
+  constexpr int A_SLOTS = (BM * 8 + 255) / 256;
+  constexpr int B_CHUNKS = CPLX ? 128 : 64;     // 16-byte chunks per B row
+  constexpr int B_ROWS = 256 / B_CHUNKS;        // B rows covered by one slot
+  constexpr int B_STRIDE = CPLX ? B_STRIDE_C : B_STRIDE_R;
+  constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned a_dst0 = smem_u32 + ((tid >> 3) * A_STRIDE + (tid & 7) * 2) * 8;
+  const unsigned b_dst0 =
+      smem_u32 + (A_TILE + (tid / B_CHUNKS) * B_STRIDE + (tid % B_CHUNKS) * 2) * 8;
+  const double *a_thr = A + a_col0 + (int64_t)(tid >> 3) * lda + (tid & 7) * 2;
+  const double2 *b_thr = B + (int64_t)(tid / B_CHUNKS) * ldb + (tid % B_CHUNKS);
+  const int64_t b_stage_stride = (int64_t)(CPLX ? KSTEP / 2 : KSTEP) * ldb;
+
+  int ld_mb = (int)(blockIdx.x % nmb);
+  int64_t ld_nb = blockIdx.x / nmb;
+  int ld_kt = 0, ld_stage = 0;
+  const double *a_src = a_thr + (int64_t)(ld_mb * BM) * lda;
+  const double2 *b_src = b_thr + ld_nb * TILE_DETS;
   auto issue_load = [&]() {
-    double *As = smem + ld_stage * STAGE_DOUBLES;
-    double *Bs = As + A_TILE;
-    const int k0 = ld_kt * KSTEP;
+    const unsigned sa = a_dst0 + ld_stage * STAGE_BYTES;
+    const unsigned sb = b_dst0 + ld_stage * STAGE_BYTES;
 #pragma unroll
-    for (int i = 0; i < (BM * 8 + 255) / 256; ++i) {
-      const int c = tid + i * 256;
-      const int row = c >> 3, cc = c & 7;
-      if ((BM * 8) % 256 == 0 || row < BM)
-        cp_async16(As + row * A_STRIDE + cc * 2, ld_A + (int64_t)row * lda + k0 + cc * 2);
+    for (int i = 0; i < A_SLOTS; ++i) {
+      if ((BM * 8) % 256 == 0 || i < A_SLOTS - 1 || (tid >> 3) + i * 32 < BM)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                         sa + i * 32 * A_STRIDE * 8),
+                     "l"(a_src + (int64_t)(i * 32) * lda));
     }
-    if (CPLX) {
-      const int r0 = k0 >> 1;  // 8 complex rows of D per stage
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = tid + i * 256;
-        const int row = c >> 7, cc = c & 127;
-        cp_async16(Bs + row * B_STRIDE_C + cc * 2, ld_B + (int64_t)(r0 + row) * ldb + cc);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = tid + i * 256;
-        const int row = c >> 6, cc = c & 63;
-        cp_async16(Bs + row * B_STRIDE_R + cc * 2, ld_B + (int64_t)(k0 + row) * ldb + cc);
-      }
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                       sb + i * B_ROWS * B_STRIDE * 8),
+                   "l"(b_src + (int64_t)(i * B_ROWS) * ldb));
     }
     ld_stage = (ld_stage + 1 == STAGES) ? 0 : ld_stage + 1;
+    a_src += KSTEP;
+    b_src += b_stage_stride;
     if (++ld_kt == nk) {
       ld_kt = 0;
-      ld_tile += gridDim.x;
-      ld_A = A + (int64_t)((int)(ld_tile % nmb) * BM) * lda + a_col0;
-      ld_B = B + (ld_tile / nmb) * TILE_DETS;
+      ld_mb += mb_step;
+      ld_nb += nb_step;
+      if (ld_mb >= nmb) {
+        ld_mb -= nmb;
+        ld_nb += 1;
+      }
+      a_src = a_thr + (int64_t)(ld_mb * BM) * lda;
+      b_src = b_thr + ld_nb * TILE_DETS;
     }
   };
 
@@ -171,9 +186,10 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
   }
 
   // ---- consumer state ------------------------------------------------------------------
-  int64_t tile = blockIdx.x;
+  int mb = (int)(blockIdx.x % nmb);
+  int64_t nb = blockIdx.x / nmb;
   int kt = 0, stage = 0;
-  int m0 = (int)(tile % nmb) * BM;
+  int m0 = mb * BM;
   int mt_active = (m_valid - (m0 + wm0)) / 8;
   mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
 
@@ -214,7 +230,7 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
 
     if (++kt == nk) {
       // ---- epilogue of this tile: interleaved complex128, 16-byte stores -----------
-      const int64_t n0 = (tile / nmb) * TILE_DETS;
+      const int64_t n0 = nb * TILE_DETS;
       if (CPLX) {
 #pragma unroll
         for (int p = 0; p < WM / 2; ++p) {
@@ -249,8 +265,13 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
 #pragma unroll
         for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       kt = 0;
-      tile += gridDim.x;
-      m0 = (int)(tile % nmb) * BM;
+      mb += mb_step;
+      nb += nb_step;
+      if (mb >= nmb) {
+        mb -= nmb;
+        nb += 1;
+      }
+      m0 = mb * BM;
       mt_active = (m_valid - (m0 + wm0)) / 8;
       mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
     }
