@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the second operator class (complex-Hermitian) leg")
+    ap.add_argument("--verify", action="store_true",
+                    help="also build sigma unsharded on every rank and report the relative "
+                    "difference to the sharded + allreduced result")
     ap.add_argument("--cpu-budget", type=float, default=15.0,
                     help="seconds of CPU work per reference sample")
     return ap.parse_args()
@@ -259,6 +262,11 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     checksum = float(torch.view_as_real(sigma).abs().sum().item())
+    verify = None
+    if args.verify:
+        full = sector.apply_operator(op)
+        verify = float((torch.linalg.norm(sigma - full) / torch.linalg.norm(full)).item())
+        del full
     del sigma
 
     result = {
@@ -266,7 +274,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         "ms_total": ms_max, "launches": int(launches),
         "phase_ms": [float(x) for x in ms3], "phase_launches": [int(x) for x in cnt3],
         "rows": rows, "pairs": pairs, "la": la, "lb": lb, "clocks": clocks,
-        "checksum": checksum,
+        "checksum": checksum, "verify": verify,
     }
 
     if do_e2e:
@@ -376,6 +384,7 @@ def run_b200(args):
                 main["op_kind"]] + (", pair-symmetric" if main["op_sym"] else ""),
         },
         "gpu_launches": main["launches"],
+        "verify_rel_err": main["verify"],
         "clocks": main["clocks"],
         "e2e": {"value": args.steps / main["e2e_s"], "unit": "sigma/s",
                 "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},

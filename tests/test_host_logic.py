@@ -1,0 +1,109 @@
+"""Host-side logic that needs no GPU: Hamiltonian containers, electron counting,
+shard arithmetic, synthetic inputs."""
+import numpy as np
+import pytest
+
+from fqe_b200 import synth
+from fqe_b200.distributed import shard_plan, split_even
+from fqe_b200.hamiltonians import diagonal_coulomb, restricted_hamiltonian
+from fqe_b200.wavefunction import alpha_beta_electrons, build_hamiltonian
+from oracle import fqe_oracle as O
+
+
+def test_alpha_beta_electrons():
+    assert alpha_beta_electrons(4, 0) == (2, 2)
+    assert alpha_beta_electrons(5, 1) == (3, 2)
+    assert alpha_beta_electrons(3, -3) == (0, 3)
+    for bad in [(-1, 0), (2, 4), (3, 0)]:
+        with pytest.raises(ValueError):
+            alpha_beta_electrons(*bad)
+
+
+def test_restricted_hamiltonian_container():
+    h1, h2 = synth.integrals(4, "herm")
+    ham = restricted_hamiltonian.RestrictedHamiltonian((h1, h2), e_0=1.5)
+    assert ham.dim() == 4 and ham.rank() == 4 and not ham.quadratic()
+    assert ham.e_0() == 1.5 and ham.conserve_number()
+    assert not ham.diagonal() and not ham.diagonal_coulomb()
+    t = ham.tensors()
+    assert t[0] is h1 and t[1] is h2
+    i1, i2 = ham.iht(0.3)
+    assert np.array_equal(i1, -0.3j * h1) and np.array_equal(i2, -0.3j * h2)
+    assert ham == restricted_hamiltonian.RestrictedHamiltonian((h1.copy(), h2.copy()), e_0=1.5)
+    assert ham != restricted_hamiltonian.RestrictedHamiltonian((h1, h2), e_0=0.0)
+    quad = restricted_hamiltonian.RestrictedHamiltonian((h1,))
+    assert quad.quadratic() and quad.rank() == 2
+    w, v = np.linalg.eigh(h1)
+    assert np.allclose(quad.transform(quad.calc_diag_transform()), np.diag(w))
+    with pytest.raises(TypeError):
+        restricted_hamiltonian.RestrictedHamiltonian(([1, 2],))
+    with pytest.raises(ValueError):
+        restricted_hamiltonian.RestrictedHamiltonian((np.zeros((2, 2, 2)),))
+
+
+def test_diagonal_coulomb_container_matches_oracle():
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((5, 5))
+    dc = diagonal_coulomb.DiagonalCoulomb(v, e_0=-0.5)
+    assert dc.diagonal_coulomb() and dc.rank() == 4 and dc.dim() == 5
+    assert np.array_equal(dc._tensor[1], np.zeros(5)) and dc._tensor[2] is v
+    h4 = rng.standard_normal((5,) * 4)
+    dc4 = diagonal_coulomb.DiagonalCoulomb(h4)
+    diag, vij = O.dc_tensors(h4)
+    assert np.array_equal(dc4._tensor[1], diag) and np.array_equal(dc4._tensor[2], vij)
+    d, a = dc.iht(0.1)
+    assert np.array_equal(a, -0.1j * v) and np.array_equal(d, np.zeros(5))
+    with pytest.raises(ValueError):
+        diagonal_coulomb.DiagonalCoulomb(np.zeros((2, 2, 2)))
+
+
+def test_build_hamiltonian_dispatch():
+    h1, h2 = synth.integrals(3, "real8")
+    ham = build_hamiltonian((h1, h2), norb=3)
+    assert isinstance(ham, restricted_hamiltonian.RestrictedHamiltonian) and ham.e_0() == 0
+    assert build_hamiltonian(ham) is ham
+    with pytest.raises(NotImplementedError):
+        build_hamiltonian((np.zeros((6, 6)),), norb=3)
+    with pytest.raises(TypeError):
+        build_hamiltonian("a+ a", norb=3)
+    with pytest.raises(TypeError):
+        build_hamiltonian(([1.0],), norb=3)
+
+
+def test_split_even_and_shard_plan():
+    for total, world, align in [(12870, 8, 1), (136, 8, 16), (256, 8, 16), (36, 4, 2), (7, 3, 1),
+                                (5, 8, 1)]:
+        parts = split_even(total, world, align)
+        assert parts[0][0] == 0 and parts[-1][1] == total
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c and a <= b
+        for lo, hi in parts[:-1]:
+            assert hi % align == 0 or hi == total
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(s for s in sizes) <= align + align
+    rows, pairs = shard_plan("det", 3, 8, 12870, 136)
+    assert pairs == (0, 136) and rows == split_even(12870, 8)[3]
+    rows, pairs = shard_plan("pair", 1, 8, 12870, 256)
+    assert rows == (0, 12870) and pairs == (32, 64)
+    rows, pairs = shard_plan("pair", 7, 8, 12870, 136)
+    assert pairs[1] == 136 and pairs[0] % 2 == 0
+    with pytest.raises(ValueError):
+        shard_plan("rows", 0, 2, 10, 4)
+
+
+def test_synthetic_integrals_symmetry_classes():
+    h1, h2 = synth.integrals(5, "real8")
+    assert h1.dtype == np.complex128 and np.all(h1.imag == 0) and np.array_equal(h1, h1.T)
+    h2p = -np.moveaxis(h2, 1, 2)
+    assert np.array_equal(h2p, h2p.transpose(1, 0, 2, 3))   # pair symmetric -> compressible
+    assert np.array_equal(h2p, h2p.transpose(0, 1, 3, 2))
+    assert np.array_equal(h2p, h2p.transpose(2, 3, 0, 1))
+    g = O.graph(2, 2, 5)
+    hm = O.dense_hamiltonian(g, h1, h2)
+    assert np.allclose(hm, hm.conj().T)
+    h1, h2 = synth.integrals(4, "herm")
+    g = O.graph(2, 1, 4)
+    hm = O.dense_hamiltonian(g, h1, h2)
+    assert np.allclose(hm, hm.conj().T) and np.abs(hm.imag).max() > 1e-3
+    c = synth.state(6, 4, seed=1)
+    assert abs(np.linalg.norm(c) - 1) < 1e-14 and np.array_equal(c, synth.state(6, 4, seed=1))
