@@ -28,6 +28,34 @@ namespace fqeb {
 
 constexpr int kTB = 256;  // beta strings per CTA
 
+// Loads as volatile asm: the compiler keeps them in program order, so a batch of
+// independent loads written back-to-back really is issued back-to-back (the plain
+// C++ form gets re-serialised load->use->load by the scheduler to save registers,
+// which leaves these latency-bound kernels with ~2 loads in flight per thread).
+__device__ __forceinline__ double2 ldg_c128(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_c128_if(bool pred, const double2 *p) {
+  double2 v = make_double2(0.0, 0.0);
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n @q ld.global.nc.v2.f64 {%0,%1}, [%2];\n}"
+      : "+d"(v.x), "+d"(v.y)
+      : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ int2 ldg_int2(const int2 *p) {
+  int2 v;
+  asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_int(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void axpy_sign(double2 &acc, int t, const double2 v) {
   if (t > 0) {
     acc.x += v.x;
@@ -44,45 +72,95 @@ __device__ __forceinline__ void axpy_sign(double2 &acc, int t, const double2 v) 
 // compressed tensor D_c[i>=j] = D[ij] + D[ji] of the reference's real-integral
 // branch (fqe_data.py:2336-2353) is produced directly.
 //
+// One CTA = one alpha row x 256 beta strings.  Everything that depends only on the
+// row (pair ids and the alpha sources/signs of every pair) is resolved once per CTA
+// into shared memory, so the per-element loop has a single level of dependent loads
+// (beta map entry -> C element) and can be unrolled for memory-level parallelism.
+//
 // WRITE_D: store D;  H1: accumulate sum_ij h1[ij]*D[ij] into sig (one-body term,
 // fqe_data.py:655 `einsum("ij,ijkl->kl", h1e, dvec)`; h1 needs no symmetry).
 template <bool WRITE_D, bool H1>
-__global__ void __launch_bounds__(kTB)
+__global__ void __launch_bounds__(kTB, 3)
 k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restrict__ amapT_a,
             const int32_t *__restrict__ amap_b, const double2 *__restrict__ coeff,
             double2 *__restrict__ dvec, int64_t ldd, int64_t row0, int nbt, int c0, int c1,
             const int32_t *__restrict__ pairs, const double2 *__restrict__ h1,
             double2 *__restrict__ sig) {
+  extern __shared__ int4 s_info[];  // (ij1, ij2, ta1, ta2) per pair-space index
   const int64_t tile = blockIdx.x;
   const int64_t r = tile / nbt;
+  const int64_t a = row0 + r;
+  {
+    const int32_t *__restrict__ ta_row = amapT_a + a * (int64_t)npair_total;
+    for (int c = c0 + threadIdx.x; c < c1; c += kTB) {
+      const int ij1 = pairs[2 * c], ij2 = pairs[2 * c + 1];
+      s_info[c - c0] = make_int4(ij1, ij2, ta_row[ij1], ij2 >= 0 ? ta_row[ij2] : 0);
+    }
+  }
+  __syncthreads();
   const int64_t b = (tile % nbt) * kTB + threadIdx.x;
   if (b >= lenb) return;
-  const int64_t a = row0 + r;
-  const int32_t *__restrict__ ta_row = amapT_a + a * (int64_t)npair_total;
   const double2 *__restrict__ crow = coeff + a * lenb;
+  const double2 *__restrict__ ccol = coeff + b;
+  const int32_t *__restrict__ mb = amap_b + b;
   double2 *__restrict__ dout = dvec + r * lenb + b;
   double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 2
-  for (int c = c0; c < c1; ++c) {
-    double2 tot = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ij = pairs[2 * c + h];  // warp-uniform
-      if (ij < 0) continue;
-      const int ta = ta_row[ij];                         // warp-uniform
-      const int tb = amap_b[(int64_t)ij * lenb + b];     // coalesced
-      double2 val = make_double2(0.0, 0.0);
-      if (ta != 0) axpy_sign(val, ta, coeff[(int64_t)(abs(ta) - 1) * lenb + b]);
-      if (tb != 0) axpy_sign(val, tb, crow[abs(tb) - 1]);
-      tot.x += val.x;
-      tot.y += val.y;
-      if (H1) {
-        const double2 hh = h1[ij];
-        acc.x += hh.x * val.x - hh.y * val.y;
-        acc.y += hh.x * val.y + hh.y * val.x;
+  // Two pair-space rows per trip, in three phases so that the four beta-map loads and
+  // then the (up to) eight C loads are all in flight together.
+  for (int c = c0; c < c1; c += 2) {
+    const bool two = (c + 1 < c1);
+    const int4 i0 = s_info[c - c0];
+    const int4 i1 = two ? s_info[c + 1 - c0] : make_int4(0, -1, 0, 0);
+    // phase 1: beta map entries
+    // (absent pairs read entry 0 of the map and are masked: keeps the batch branch-free)
+    const int tb00 = ldg_int(mb + (int64_t)i0.x * lenb);
+    const int tb01 = (i0.y >= 0) ? ldg_int(mb + (int64_t)i0.y * lenb) : 0;
+    const int tb10 = two ? ldg_int(mb + (int64_t)i1.x * lenb) : 0;
+    const int tb11 = (i1.y >= 0) ? ldg_int(mb + (int64_t)i1.y * lenb) : 0;
+    const int ta00 = i0.z, ta01 = i0.w, ta10 = two ? i1.z : 0, ta11 = i1.w;
+    // phase 2: C elements (predicated loads)
+    const double2 va00 = ldg_c128_if(ta00 != 0, ccol + (int64_t)(abs(ta00) - 1) * lenb);
+    const double2 va01 = ldg_c128_if(ta01 != 0, ccol + (int64_t)(abs(ta01) - 1) * lenb);
+    const double2 va10 = ldg_c128_if(ta10 != 0, ccol + (int64_t)(abs(ta10) - 1) * lenb);
+    const double2 va11 = ldg_c128_if(ta11 != 0, ccol + (int64_t)(abs(ta11) - 1) * lenb);
+    const double2 vb00 = ldg_c128_if(tb00 != 0, crow + (abs(tb00) - 1));
+    const double2 vb01 = ldg_c128_if(tb01 != 0, crow + (abs(tb01) - 1));
+    const double2 vb10 = ldg_c128_if(tb10 != 0, crow + (abs(tb10) - 1));
+    const double2 vb11 = ldg_c128_if(tb11 != 0, crow + (abs(tb11) - 1));
+    // phase 3: signed sums (multiplying by +-1.0 is exact)
+    auto sgn = [](int t) { return t < 0 ? -1.0 : 1.0; };
+    const double2 d00 = make_double2(sgn(ta00) * va00.x + sgn(tb00) * vb00.x,
+                                     sgn(ta00) * va00.y + sgn(tb00) * vb00.y);
+    const double2 d01 = make_double2(sgn(ta01) * va01.x + sgn(tb01) * vb01.x,
+                                     sgn(ta01) * va01.y + sgn(tb01) * vb01.y);
+    const double2 d10 = make_double2(sgn(ta10) * va10.x + sgn(tb10) * vb10.x,
+                                     sgn(ta10) * va10.y + sgn(tb10) * vb10.y);
+    const double2 d11 = make_double2(sgn(ta11) * va11.x + sgn(tb11) * vb11.x,
+                                     sgn(ta11) * va11.y + sgn(tb11) * vb11.y);
+    if (WRITE_D) {
+      dout[(int64_t)(c - c0) * ldd] = make_double2(d00.x + d01.x, d00.y + d01.y);
+      if (two) dout[(int64_t)(c + 1 - c0) * ldd] = make_double2(d10.x + d11.x, d10.y + d11.y);
+    }
+    if (H1) {
+      const double2 h00 = h1[i0.x];
+      acc.x += h00.x * d00.x - h00.y * d00.y;
+      acc.y += h00.x * d00.y + h00.y * d00.x;
+      if (i0.y >= 0) {
+        const double2 h01 = h1[i0.y];
+        acc.x += h01.x * d01.x - h01.y * d01.y;
+        acc.y += h01.x * d01.y + h01.y * d01.x;
+      }
+      if (two) {
+        const double2 h10 = h1[i1.x];
+        acc.x += h10.x * d10.x - h10.y * d10.y;
+        acc.y += h10.x * d10.y + h10.y * d10.x;
+        if (i1.y >= 0) {
+          const double2 h11 = h1[i1.y];
+          acc.x += h11.x * d11.x - h11.y * d11.y;
+          acc.y += h11.x * d11.y + h11.y * d11.x;
+        }
       }
     }
-    if (WRITE_D) dout[(int64_t)(c - c0) * ldd] = tot;
   }
   if (H1) {
     double2 s = sig[a * lenb + b];
@@ -92,47 +170,112 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
   }
 }
 
-__global__ void __launch_bounds__(kTB)
-k_make_coeff(int npair, int64_t lena, int64_t lenb, const int32_t *__restrict__ amapT_a,
-             const int32_t *__restrict__ amap_b, const int32_t *__restrict__ rowmap,
-             const double2 *__restrict__ evec, int64_t lde, int64_t row0, int64_t nrows, int nbt,
-             double2 z, double2 *__restrict__ out) {
+// Scatter, by target.  One CTA = one target alpha row x 256 beta strings.
+//   alpha part: the lk_a non-vanishing excitations of row x are filtered ONCE per CTA
+//               against the chunk's row range (ordered, deterministic compaction into
+//               shared memory); the element loop then only visits real hits.
+//   beta part : compact per-column excitation lists clist_b[slot][b] (coalesced) give
+//               exactly lk_b gathers per element instead of norb^2 table probes.
+__global__ void __launch_bounds__(kTB, 3)
+k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
+             const int2 *__restrict__ clistT_a, const int2 *__restrict__ clist_b,
+             const int32_t *__restrict__ rowmap, const double2 *__restrict__ evec, int64_t lde,
+             int64_t row0, int64_t nrows, int nbt, double2 z, double2 *__restrict__ out) {
+  extern __shared__ int s_mem[];
+  int *s_rowmap = s_mem;                                   // [npair]
+  int2 *s_hits = reinterpret_cast<int2 *>(s_mem + ((npair + 1) & ~1));  // [lk_a]
+  __shared__ int s_wcount[kTB / 32];
+  __shared__ int s_nhit;
   const int64_t tile = blockIdx.x;
   const int64_t x = tile / nbt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = threadIdx.x; p < npair; p += kTB) s_rowmap[p] = rowmap[p];
+  if (threadIdx.x == 0) s_nhit = 0;
+  __syncthreads();
+  // ordered compaction of the alpha hits of row x that fall into [row0, row0+nrows)
+  for (int base = 0; base < lk_a; base += kTB) {
+    const int slot = base + threadIdx.x;
+    int2 e = make_int2(0, 0);
+    bool hit = false;
+    if (slot < lk_a) {
+      e = clistT_a[x * (int64_t)lk_a + slot];
+      const int64_t y = (int64_t)(abs(e.y) - 1) - row0;
+      hit = (y >= 0 && y < nrows);
+      if (hit) e = make_int2(s_rowmap[e.x], e.y > 0 ? (int)(y + 1) : -(int)(y + 1));
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_wcount[warp] = __popc(ballot);
+    __syncthreads();
+    int offset = s_nhit;
+    for (int w = 0; w < warp; ++w) offset += s_wcount[w];
+    if (hit) s_hits[offset + __popc(ballot & ((1u << lane) - 1u))] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < kTB / 32; ++w) tot += s_wcount[w];
+      s_nhit += tot;
+    }
+    __syncthreads();
+  }
+  const int nhit = s_nhit;
+  const int64_t xr = x - row0;
+  const bool in_chunk = (xr >= 0 && xr < nrows);
+  if (nhit == 0 && !in_chunk) return;
   const int64_t b = (tile % nbt) * kTB + threadIdx.x;
   if (b >= lenb) return;
-  const int32_t *__restrict__ ta_row = amapT_a + x * (int64_t)npair;
   double2 acc = make_double2(0.0, 0.0);
-  bool touched = false;
-  // alpha: rows of E that live in this chunk and map onto row x
-#pragma unroll 4
-  for (int kl = 0; kl < npair; ++kl) {
-    const int ta = ta_row[kl];  // warp-uniform
-    if (ta != 0) {
-      const int64_t y = (int64_t)(abs(ta) - 1) - row0;
-      if (y >= 0 && y < nrows) {
-        touched = true;
-        axpy_sign(acc, ta, evec[(int64_t)rowmap[kl] * lde + y * lenb + b]);
+  const double2 *__restrict__ ecol = evec + b;
+  // batches: all loads of a batch are issued before any is consumed (memory-level
+  // parallelism); signs are applied as exact multiplications by +-1.0
+  constexpr int UA = 4, UB = 8;
+  int h = 0;
+  for (; h + UA <= nhit; h += UA) {
+    double2 v[UA];
+    double sg[UA];
+#pragma unroll
+    for (int u = 0; u < UA; ++u) {
+      const int2 e = s_hits[h + u];
+      v[u] = ldg_c128(ecol + (int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * lenb);
+      sg[u] = e.y < 0 ? -1.0 : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UA; ++u) {
+      acc.x += sg[u] * v[u].x;
+      acc.y += sg[u] * v[u].y;
+    }
+  }
+  for (; h < nhit; ++h) {
+    const int2 e = s_hits[h];
+    axpy_sign(acc, e.y, ecol[(int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * lenb]);
+  }
+  if (in_chunk) {
+    const double2 *__restrict__ erow = evec + xr * lenb;
+    const int2 *__restrict__ cl = clist_b + b;
+    int slot = 0;
+    for (; slot + UB <= lk_b; slot += UB) {
+      int2 e[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) e[u] = ldg_int2(cl + (int64_t)(slot + u) * lenb);
+      double2 v[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        v[u] = ldg_c128(erow + (int64_t)s_rowmap[e[u].x] * lde + (abs(e[u].y) - 1));
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const double sg = e[u].y < 0 ? -1.0 : 1.0;
+        acc.x += sg * v[u].x;
+        acc.y += sg * v[u].y;
       }
     }
-  }
-  // beta: only rows of the chunk itself
-  const int64_t xr = x - row0;
-  if (xr >= 0 && xr < nrows) {
-    touched = true;
-    const double2 *__restrict__ erow = evec + xr * lenb;
-#pragma unroll 4
-    for (int kl = 0; kl < npair; ++kl) {
-      const int tb = amap_b[(int64_t)kl * lenb + b];
-      if (tb != 0) axpy_sign(acc, tb, erow[(int64_t)rowmap[kl] * lde + (abs(tb) - 1)]);
+    for (; slot < lk_b; ++slot) {
+      const int2 e = cl[(int64_t)slot * lenb];
+      axpy_sign(acc, e.y, erow[(int64_t)s_rowmap[e.x] * lde + (abs(e.y) - 1)]);
     }
   }
-  if (touched) {
-    double2 s = out[x * lenb + b];
-    s.x += z.x * acc.x - z.y * acc.y;
-    s.y += z.x * acc.y + z.y * acc.x;
-    out[x * lenb + b] = s;
-  }
+  double2 s = out[x * lenb + b];
+  s.x += z.x * acc.x - z.y * acc.y;
+  s.y += z.x * acc.y + z.y * acc.x;
+  out[x * lenb + b] = s;
 }
 
 // pairs == nullptr: identity pair list of the graph (D row c <-> pair c), np_eff = norb^2
@@ -158,10 +301,16 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
   double2 *d = (double2 *)d_dvec;
   const double2 *h1 = (const double2 *)d_h1;
   double2 *sig = (double2 *)d_sig;
-#define FQEB_LAUNCH_DVEC(WD, HH)                                                              \
-  k_make_dvec<WD, HH><<<(unsigned)tiles, kTB, 0, st>>>(npair_full, lena, lenb, g->d_amapT[0], \
-                                                       g->d_amap[1], c, d, ldd, row0, nbt,    \
-                                                       ij0, ij1, d_pairs, h1, sig)
+  const size_t smem = sizeof(int4) * (size_t)(ij1 - ij0);
+#define FQEB_LAUNCH_DVEC(WD, HH)                                                               \
+  do {                                                                                         \
+    if (smem > 48 * 1024)                                                                      \
+      FQEB_CUDA(cudaFuncSetAttribute(k_make_dvec<WD, HH>,                                      \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_make_dvec<WD, HH><<<(unsigned)tiles, kTB, smem, st>>>(                                   \
+        npair_full, lena, lenb, g->d_amapT[0], g->d_amap[1], c, d, ldd, row0, nbt, ij0, ij1,   \
+        d_pairs, h1, sig);                                                                     \
+  } while (0)
   if (d && h1) FQEB_LAUNCH_DVEC(true, true);
   else if (d) FQEB_LAUNCH_DVEC(true, false);
   else if (h1) FQEB_LAUNCH_DVEC(false, true);
@@ -186,10 +335,13 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
   const int nbt = (int)((lenb + kTB - 1) / kTB);
   const int64_t tiles = lena * nbt;
   FQEB_REQUIRE(tiles < (1ll << 31), "make_coeff: problem too large for one launch");
-  k_make_coeff<<<(unsigned)tiles, kTB, 0, st>>>(npair, lena, lenb, g->d_amapT[0], g->d_amap[1],
-                                                d_rowmap, (const double2 *)d_evec, lde, row0,
-                                                nrows, nbt, make_double2(zr, zi),
-                                                (double2 *)d_out);
+  const size_t smem = sizeof(int) * (size_t)((npair + 1) & ~1) + sizeof(int2) * (size_t)g->lk[0];
+  if (smem > 48 * 1024)
+    FQEB_CUDA(cudaFuncSetAttribute(k_make_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  k_make_coeff<<<(unsigned)tiles, kTB, smem, st>>>(
+      npair, lena, lenb, g->lk[0], g->lk[1], g->d_clistT[0], g->d_clist[1], d_rowmap,
+      (const double2 *)d_evec, lde, row0, nrows, nbt, make_double2(zr, zi), (double2 *)d_out);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }

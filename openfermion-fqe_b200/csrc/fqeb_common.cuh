@@ -65,6 +65,11 @@ struct fqeb_graph {
   // adjoint map: amap[ij][x] = sign*(y+1) with a^+_j a_i |x> = sign |y>  (ij = i*norb+j)
   int32_t *d_amap[2];      // [norb*norb][len]
   int32_t *d_amapT[2];     // [len][norb*norb]
+  // compact lists of the lk = nele*(norb-nele+1) non-vanishing adjoint-map entries of
+  // every string, as int2 (ij, sign*(y+1)), ascending ij:
+  int lk[2];
+  int2 *d_clistT[2];       // [len][lk]   by string  (warp-uniform access per row)
+  int2 *d_clist[2];        // [lk][len]   by slot    (coalesced access per column)
   double *d_small;         // scratch for small operator uploads (diag, v, ...)
   size_t small_bytes;
   double *d_sterm[2];      // per-string diagonal-Coulomb terms, complex [len]

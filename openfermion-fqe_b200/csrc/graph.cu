@@ -110,6 +110,24 @@ __global__ void k_build_maps(int norb, int64_t len,
   amapT[x * (int64_t)(norb * norb) + p] = val;
 }
 
+// compact the non-zero adjoint-map entries of each string (exactly lk of them)
+__global__ void k_build_clists(int npair, int64_t len, int lk, const int32_t *__restrict__ amapT,
+                               int2 *__restrict__ clistT, int2 *__restrict__ clist) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= len) return;
+  const int32_t *row = amapT + x * (int64_t)npair;
+  int slot = 0;
+  for (int p = 0; p < npair && slot < lk; ++p) {
+    const int v = row[p];
+    if (v != 0) {
+      const int2 e = make_int2(p, v);
+      clistT[x * (int64_t)lk + slot] = e;
+      clist[(int64_t)slot * len + x] = e;
+      ++slot;
+    }
+  }
+}
+
 static int build_spin(fqeb_graph *g, int spin, const uint64_t *d_binom) {
   const int norb = g->norb, nele = g->nele[spin];
   const int64_t len = g->len[spin];
@@ -129,6 +147,16 @@ static int build_spin(fqeb_graph *g, int spin, const uint64_t *d_binom) {
     dim3 grid(blocks, npair);
     k_build_maps<<<grid, threads>>>(norb, len, g->d_str[spin], g->d_Z[spin], g->d_amap[spin],
                                     g->d_amapT[spin]);
+    FQEB_CHECK_LAUNCH();
+  }
+  const int lk = nele * (norb - nele + 1);
+  g->lk[spin] = lk;
+  const size_t cbytes = sizeof(int2) * (size_t)(lk > 0 ? lk : 1) * len;
+  FQEB_CUDA(cudaMalloc(&g->d_clistT[spin], cbytes));
+  FQEB_CUDA(cudaMalloc(&g->d_clist[spin], cbytes));
+  if (lk > 0) {
+    k_build_clists<<<blocks, threads>>>(npair, len, lk, g->d_amapT[spin], g->d_clistT[spin],
+                                        g->d_clist[spin]);
     FQEB_CHECK_LAUNCH();
   }
   return FQEB_OK;
@@ -195,6 +223,9 @@ extern "C" int fqeb_graph_create(int norb, int nalpha, int nbeta, fqeb_graph **o
       g->d_str[1] = g->d_str[0];
       g->d_amap[1] = g->d_amap[0];
       g->d_amapT[1] = g->d_amapT[0];
+      g->lk[1] = g->lk[0];
+      g->d_clistT[1] = g->d_clistT[0];
+      g->d_clist[1] = g->d_clist[0];
       continue;
     }
     rc = build_spin(g, spin, d_binom);
@@ -241,6 +272,8 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
     if (g->d_str[s]) cudaFree(g->d_str[s]);
     if (g->d_amap[s]) cudaFree(g->d_amap[s]);
     if (g->d_amapT[s]) cudaFree(g->d_amapT[s]);
+    if (g->d_clistT[s]) cudaFree(g->d_clistT[s]);
+    if (g->d_clist[s]) cudaFree(g->d_clist[s]);
   }
   for (int s = 0; s < 2; ++s) free(g->h_Z[s]);
   if (g->d_small) cudaFree(g->d_small);
