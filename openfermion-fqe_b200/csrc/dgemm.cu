@@ -41,6 +41,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include <vector>
 
 namespace fqeb {
@@ -73,6 +74,54 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// ---- fragment loads with compile-time offsets ------------------------------------------
+// Written as asm with an immediate offset from ONE base register per operand: left to
+// itself the compiler, short of registers next to 136 accumulator registers,
+// rematerialises every fragment address from (stage, row, lane) with 3 dependent IMADs
+// in front of each LDS (seen in SASS / ncu source view), which sits on the critical
+// path of the DMMA stream.
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned base) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF));
+  return v;
+}
+
+// All DMMAs of one pipeline stage for one warp.  a_base / b_base: shared-memory byte
+// addresses of this lane's first A / B fragment element in the stage.
+template <bool CPLX, int WM, int WN, bool RAGGED>
+__device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], unsigned a_base,
+                                          unsigned b_base, int kk_count, int mt_active) {
+  static_for<0, KSTEP / 4>([&](auto kk_c) {
+    constexpr int kk = decltype(kk_c)::value;
+    if (kk < kk_count) {
+      double bf[WN];
+      static_for<0, WN>([&](auto nt_c) {
+        constexpr int nt = decltype(nt_c)::value;
+        constexpr int off = CPLX ? (kk * 2 * B_STRIDE_C + nt * 16) * 8
+                                 : (kk * 4 * B_STRIDE_R + nt * 8) * 8;
+        bf[nt] = lds_f64<off>(b_base);
+      });
+      static_for<0, WM>([&](auto mt_c) {
+        constexpr int mt = decltype(mt_c)::value;
+        if (!RAGGED || mt < mt_active) {
+          const double af = lds_f64<(mt * 8 * A_STRIDE + kk * 4) * 8>(a_base);
+#pragma unroll
+          for (int nt = 0; nt < WN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
+        }
+      });
+    }
+  });
+}
+
 // CTA tile = BM x 128 real elements, 8 warps arranged WARPS_M x (8/WARPS_M); each
 // warp owns WM x WN DMMA (8x8) tiles.  Two shapes are instantiated:
 //   wide  WARPS_M=2, WM=8, WN=4 : 128 x 128, for row counts that are multiples of 128
@@ -92,7 +141,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // the next tile are in flight while the last stages of the current one are in the
 // tensor cores and the epilogue's stores overlap those loads; launched with one CTA
 // per tile it degenerates to the classic kernel.
-template <bool CPLX, int WARPS_M, int WM, int WN>
+template <bool CPLX, int WARPS_M, int WM, int WN, bool RAGGED>
 __global__ void __launch_bounds__(256, 1)
 k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
         int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out, int k_valid,
@@ -186,6 +235,10 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
   }
 
   // ---- consumer state ------------------------------------------------------------------
+  const unsigned a_frag_off = ((wm0 + g) * A_STRIDE + tg) * 8;
+  const unsigned b_frag_off =
+      (A_TILE + (CPLX ? (tg >> 1) * B_STRIDE_C + (wn0 + g) * 2 + (tg & 1)
+                      : tg * B_STRIDE_R + wn0 + g)) * 8;
   int mb = (int)(blockIdx.x % nmb);
   int64_t nb = blockIdx.x / nmb;
   int kt = 0, stage = 0;
@@ -198,35 +251,13 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
     __syncthreads();
     if (it + STAGES - 1 < total_it) issue_load();
     cp_async_commit();
-    const double *As = smem + stage * STAGE_DOUBLES;
-    const double *Bs = As + A_TILE;
+    const unsigned stage_u32 = smem_u32 + stage * STAGE_BYTES;
     stage = (stage + 1 == STAGES) ? 0 : stage + 1;
     // whole k4 steps of this stage that contain data
     int kk_count = (k_valid - kt * KSTEP + 3) / 4;
     kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
-#pragma unroll
-    for (int kk = 0; kk < KSTEP / 4; ++kk) {
-      if (kk < kk_count) {
-        double bf[WN];
-#pragma unroll
-        for (int nt = 0; nt < WN; ++nt) {
-          const int n = wn0 + nt * 8 + g;
-          if (CPLX) {
-            bf[nt] = Bs[(kk * 2 + (tg >> 1)) * B_STRIDE_C + n * 2 + (tg & 1)];
-          } else {
-            bf[nt] = Bs[(kk * 4 + tg) * B_STRIDE_R + n];
-          }
-        }
-#pragma unroll
-        for (int mt = 0; mt < WM; ++mt) {
-          if (mt < mt_active) {
-            const double af = As[(wm0 + mt * 8 + g) * A_STRIDE + kk * 4 + tg];
-#pragma unroll
-            for (int nt = 0; nt < WN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
-          }
-        }
-      }
-    }
+    mma_stage<CPLX, WM, WN, RAGGED>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off, kk_count,
+                                    mt_active);
 
     if (++kt == nk) {
       // ---- epilogue of this tile: interleaved complex128, 16-byte stores -----------
@@ -234,7 +265,7 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
       if (CPLX) {
 #pragma unroll
         for (int p = 0; p < WM / 2; ++p) {
-          if (2 * p < mt_active) {
+          if (!RAGGED || 2 * p < mt_active) {
             const int kl = ((m0 + wm0) >> 1) + p * 8 + g;
             if (kl < nrows_out) {
               double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
@@ -249,7 +280,7 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
       } else {
 #pragma unroll
         for (int mt = 0; mt < WM; ++mt) {
-          if (mt < mt_active) {
+          if (!RAGGED || mt < mt_active) {
             const int kl = m0 + wm0 + mt * 8 + g;
             if (kl < nrows_out) {
               double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
@@ -279,6 +310,216 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
   cp_async_wait<0>();
 }
 
+// ---- warp-specialised variant --------------------------------------------------------
+// Same tiles, same math, different plumbing: two PRODUCER warps (one streams A tiles,
+// one streams D tiles, cp.async) feed eight CONSUMER warps through a ring of STAGES
+// shared-memory slots guarded by mbarriers (full[s]: data landed, empty[s]: all
+// consumer warps are done with slot s).  There is no CTA-wide barrier in the main
+// loop: consumer warps drift apart instead of hitting their non-tensor phases (fragment
+// loads, epilogue) in lock-step, and they issue nothing but LDS + DMMA.
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned addr) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
+}
+
+template <bool CPLX, int WARPS_M, int WM, int WN, bool RAGGED>
+__global__ void __launch_bounds__(320, 1)
+k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
+           int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out,
+           int k_valid, int nmb, int64_t ntiles) {
+  constexpr int BM = WARPS_M * WM * 8;
+  constexpr int WARPS_N = 8 / WARPS_M;
+  static_assert(WARPS_N * WN * 8 == BNR, "warp layout must span 128 columns");
+  static_assert(!CPLX || (WM % 2 == 0), "complex mode pairs re/im row tiles");
+  constexpr int A_TILE = BM * A_STRIDE;
+  constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
+  constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  constexpr int TILE_DETS = CPLX ? BNR : BNR / 2;
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nk = (k_valid + KSTEP - 1) / KSTEP;
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned bar_full = smem_u32 + STAGES * STAGE_BYTES;   // STAGES x 8 bytes
+  const unsigned bar_empty = bar_full + STAGES * 8;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 64);   // 2 producer warps, one arrive per lane
+      mbar_init(bar_empty + s * 8, 8);   // one arrive per consumer warp
+    }
+  }
+  __syncthreads();
+  if ((int64_t)blockIdx.x >= ntiles) return;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t total_it = my_tiles * nk;
+  const int mb_step = (int)(gridDim.x % nmb);
+  const int64_t nb_step = gridDim.x / nmb;
+  int mb = (int)(blockIdx.x % nmb);
+  int64_t nb = blockIdx.x / nmb;
+
+  if (warp >= 8) {
+    // =========================== producers ===========================================
+    const bool loads_a = (warp == 8);
+    constexpr int B_CHUNKS = CPLX ? 128 : 64;   // 16-byte chunks per B row
+    constexpr int B_STRIDE = CPLX ? B_STRIDE_C : B_STRIDE_R;
+    constexpr int B_SUB = B_CHUNKS / 32;        // lane-strided pieces per B row
+    constexpr int B_ROWS_STAGE = CPLX ? KSTEP / 2 : KSTEP;
+    // A: chunk id = lane + 32*i -> row = 4*i + lane/8, 16-byte column = lane%8
+    const unsigned a_dst0 = smem_u32 + ((lane >> 3) * A_STRIDE + (lane & 7) * 2) * 8;
+    const double *a_thr = A + a_col0 + (int64_t)(lane >> 3) * lda + (lane & 7) * 2;
+    // B: piece j of row r -> chunk lane + 32*j
+    const unsigned b_dst0 = smem_u32 + (A_TILE + lane * 2) * 8;
+    const double2 *b_thr = B + lane;
+    int kt = 0, stage = 0;
+    unsigned round_parity = 1;  // parity of (round-1) with round = 0 -> no wait first time
+    bool first_round = true;
+    const double *a_src = a_thr + (int64_t)(mb * BM) * lda;
+    const double2 *b_src = b_thr + nb * TILE_DETS;
+    for (int64_t it = 0; it < total_it; ++it) {
+      if (!first_round) mbar_wait(bar_empty + stage * 8, round_parity);
+      const unsigned sbase = stage * STAGE_BYTES;
+      if (loads_a) {
+#pragma unroll 8
+        for (int i = 0; i < BM / 4; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                           a_dst0 + sbase + i * 4 * A_STRIDE * 8),
+                       "l"(a_src + (int64_t)(i * 4) * lda));
+      } else {
+#pragma unroll 8
+        for (int i = 0; i < B_ROWS_STAGE * B_SUB; ++i) {
+          const int r = i / B_SUB, j = i % B_SUB;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                           b_dst0 + sbase + (r * B_STRIDE + j * 64) * 8),
+                       "l"(b_src + (int64_t)r * ldb + j * 32));
+        }
+      }
+      cp_async_mbar_arrive(bar_full + stage * 8);
+      a_src += KSTEP;
+      b_src += (int64_t)B_ROWS_STAGE * ldb;
+      if (++stage == STAGES) {
+        stage = 0;
+        round_parity ^= 1;
+        first_round = false;
+      }
+      if (++kt == nk) {
+        kt = 0;
+        mb += mb_step;
+        nb += nb_step;
+        if (mb >= nmb) {
+          mb -= nmb;
+          nb += 1;
+        }
+        a_src = a_thr + (int64_t)(mb * BM) * lda;
+        b_src = b_thr + nb * TILE_DETS;
+      }
+    }
+    asm volatile("cp.async.wait_all;\n" ::);
+    return;
+  }
+
+  // ============================= consumers =============================================
+  const int g = lane >> 2, tg = lane & 3;
+  const int wm0 = (warp / WARPS_N) * (WM * 8);
+  const int wn0 = (warp % WARPS_N) * (WN * 8);
+  const unsigned a_frag_off = ((wm0 + g) * A_STRIDE + tg) * 8;
+  const unsigned b_frag_off =
+      (A_TILE + (CPLX ? (tg >> 1) * B_STRIDE_C + (wn0 + g) * 2 + (tg & 1)
+                      : tg * B_STRIDE_R + wn0 + g)) * 8;
+  double acc[WM][WN][2];
+#pragma unroll
+  for (int i = 0; i < WM; ++i)
+#pragma unroll
+    for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  int kt = 0, stage = 0;
+  unsigned parity = 0;
+  int m0 = mb * BM;
+  int mt_active = (m_valid - (m0 + wm0)) / 8;
+  mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
+
+  for (int64_t it = 0; it < total_it; ++it) {
+    mbar_wait(bar_full + stage * 8, parity);
+    const unsigned stage_u32 = smem_u32 + stage * STAGE_BYTES;
+    int kk_count = (k_valid - kt * KSTEP + 3) / 4;
+    kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
+    mma_stage<CPLX, WM, WN, RAGGED>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off, kk_count,
+                                    mt_active);
+    // release the slot: every lane's fragment loads have been consumed by its DMMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + stage * 8);
+    if (++stage == STAGES) {
+      stage = 0;
+      parity ^= 1;
+    }
+
+    if (++kt == nk) {
+      const int64_t n0 = nb * TILE_DETS;
+      if (CPLX) {
+#pragma unroll
+        for (int p = 0; p < WM / 2; ++p) {
+          if (!RAGGED || 2 * p < mt_active) {
+            const int kl = ((m0 + wm0) >> 1) + p * 8 + g;
+            if (kl < nrows_out) {
+              double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
+#pragma unroll
+              for (int nt = 0; nt < WN; ++nt) {
+                erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
+                erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < WM; ++mt) {
+          if (!RAGGED || mt < mt_active) {
+            const int kl = m0 + wm0 + mt * 8 + g;
+            if (kl < nrows_out) {
+              double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
+#pragma unroll
+              for (int nt = 0; nt < WN; ++nt)
+                erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      kt = 0;
+      mb += mb_step;
+      nb += nb_step;
+      if (mb >= nmb) {
+        mb -= nmb;
+        nb += 1;
+      }
+      m0 = mb * BM;
+      mt_active = (m_valid - (m0 + wm0)) / 8;
+      mt_active = mt_active < 0 ? 0 : (mt_active > WM ? WM : mt_active);
+    }
+  }
+}
+
 // ---- tile-shape menu ---------------------------------------------------------------
 struct GemmShape {
   int warps_m, wm;
@@ -291,11 +532,27 @@ static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int
                         double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
                         cudaStream_t st) {
   constexpr int BM = WARPS_M * WM * 8;
-  constexpr size_t SMEM = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES;
+  // + 2*STAGES mbarriers (used by the warp-specialised variant only)
+  constexpr size_t SMEM =
+      sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES + 16 * STAGES;
+  // FQEB_GEMM_WS=0 selects the classic (all warps load and compute) variant
+  static const bool ws = !(getenv("FQEB_GEMM_WS") && getenv("FQEB_GEMM_WS")[0] == '0');
   static bool attr_set = false;
-  auto kern = k_dgemm<CPLX, WARPS_M, WM, WN>;
+  // RAGGED: the last row block is partial, per-tile predicates on the row tiles
+  const bool ragged = (m_valid % BM) != 0;
+  auto kern = ws ? (ragged ? k_dgemm_ws<CPLX, WARPS_M, WM, WN, true>
+                           : k_dgemm_ws<CPLX, WARPS_M, WM, WN, false>)
+                 : (ragged ? k_dgemm<CPLX, WARPS_M, WM, WN, true>
+                           : k_dgemm<CPLX, WARPS_M, WM, WN, false>);
   if (!attr_set) {
-    FQEB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
   const int nmb = (m_valid + BM - 1) / BM;
@@ -311,7 +568,7 @@ static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int
     if (grid > tiles) grid = tiles;
   }
   FQEB_REQUIRE(grid < (1ll << 31), "contract: too many tiles for one launch");
-  kern<<<(unsigned)grid, 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+  kern<<<(unsigned)grid, ws ? 320 : 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
                                           (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
                                           tiles);
   FQEB_CHECK_LAUNCH();
