@@ -41,6 +41,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <type_traits>
 #include <vector>
 
@@ -72,6 +73,20 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int ldg_int_g(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_c128_if_g(bool pred, const double2 *p) {
+  double2 v = make_double2(0.0, 0.0);
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n @q ld.global.nc.v2.f64 {%0,%1}, [%2];\n}"
+      : "+d"(v.x), "+d"(v.y)
+      : "l"(p), "r"((int)pred));
+  return v;
 }
 
 // ---- fragment loads with compile-time offsets ------------------------------------------
@@ -595,6 +610,287 @@ static GemmShape pick_shape(bool cplx, int m_valid) {
   return best;
 }
 
+// ---- fused gather + contraction ----------------------------------------------------------
+// The D tensor is never written to HBM: four PRODUCER warps build each 16-pair x 64-
+// determinant tile of D directly in the shared-memory ring (signed gathers from C,
+// exactly what k_make_dvec computes) while the eight CONSUMER warps run the DMMA
+// stream on the previous tiles.  Applies when one CTA covers all rows of the operator
+// (pair space <= 144, real/imaginary class: norb=16 with real-orbital integrals) so that
+// no D tile is gathered twice.  The one-body term is folded into the operand beforehand
+// (h2'[ij,kk] += h1'[ij]/n_elec, exact on a fixed-particle-number sector), so sigma gets
+// everything through E.  Saves writing and re-reading D (2 x 360 GB per sigma at
+// norb=16) and the whole gather launch.
+//
+// Column space: determinants of a chunk are laid out with a row pitch that is a multiple
+// of 64, so a tile never straddles two alpha rows:  col = r*pitch + b.
+template <int WM, bool RAGGED>
+__global__ void __launch_bounds__(384, 1)
+k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, int k_valid,
+              const int32_t *__restrict__ pairs, const int32_t *__restrict__ amapT_a,
+              const int32_t *__restrict__ amap_b, int npair_total,
+              const double2 *__restrict__ coeff, int64_t lenb, int64_t row0, int pitch,
+              int tiles_per_row, double2 *__restrict__ E, int64_t lde, int m_valid,
+              int nrows_out, int64_t ntiles) {
+  constexpr int WN = 2;
+  constexpr int BM = WM * 8;
+  constexpr int A_TILE = BM * A_STRIDE;
+  constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
+  constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  constexpr int TILE_DETS = BNR / 2;  // 64
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nk = (k_valid + KSTEP - 1) / KSTEP;
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned bar_full = smem_u32 + STAGES * STAGE_BYTES;
+  const unsigned bar_empty = bar_full + STAGES * 8;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 64);   // one producer warp: 32 lanes x (cp.async arrive + arrive)
+      mbar_init(bar_empty + s * 8, 8);   // one arrive per consumer warp
+    }
+  }
+  __syncthreads();
+  if ((int64_t)blockIdx.x >= ntiles) return;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  int64_t nb = blockIdx.x;
+
+  if (warp >= 8) {
+    // =========================== producers ===========================================
+    // Stage-parallel: producer warp w fills ring slots w, w+4, ... on its own (operand
+    // tile by cp.async, D tile by signed gathers), so each warp has STAGES consumer
+    // stage-times to hide its global-load latency.  Lane l owns determinants l and l+32
+    // of the 64-determinant tile and walks the 16 pair rows of the stage in batches of
+    // two rows; the map lookups of batch q+1 are issued before batch q is combined.
+    const int pw = warp - 8;           // 0..3 == ring slot owned
+    const unsigned a_dst0 = smem_u32 + ((lane >> 3) * A_STRIDE + (lane & 7) * 2) * 8;
+    const double *a_src0 = A + a_col0 + (int64_t)(lane >> 3) * lda + (lane & 7) * 2;
+    const unsigned b_dst0 = smem_u32 + (A_TILE + 2 * lane) * 8;
+    const unsigned sbase = pw * STAGE_BYTES;
+    const unsigned full_bar = bar_full + pw * 8, empty_bar = bar_empty + pw * 8;
+    unsigned round_parity = 1;
+    bool first_round = true;
+    const int64_t total_it = my_tiles * nk;
+    // position of this warp's first stage
+    int64_t t = pw / nk;
+    int kt = pw % nk;
+    nb += t * gridDim.x;
+    for (int64_t it = pw; it < total_it; it += STAGES) {
+      const int r = (int)(nb / tiles_per_row);
+      const int bt = (int)(nb - (int64_t)r * tiles_per_row);
+      const int64_t a = row0 + r;
+      const int64_t b0 = (int64_t)bt * TILE_DETS + lane;
+      const int64_t b1 = b0 + 32;
+      const bool v0 = b0 < lenb, v1 = b1 < lenb;
+      const int32_t *__restrict__ ta_row = amapT_a + a * (int64_t)npair_total;
+      const double2 *__restrict__ crow = coeff + a * lenb;
+      const double2 *__restrict__ ccol0 = coeff + (v0 ? b0 : 0);
+      const double2 *__restrict__ ccol1 = coeff + (v1 ? b1 : 0);
+      const int32_t *__restrict__ mb0 = amap_b + (v0 ? b0 : 0);
+      const int32_t *__restrict__ mb1 = amap_b + (v1 ? b1 : 0);
+
+      if (!first_round) mbar_wait(empty_bar, round_parity);
+      // operand tile: BM rows x 8 chunks, 4 rows per pass of the warp
+      {
+        const double *a_src = a_src0 + kt * KSTEP;
+#pragma unroll 6
+        for (int i = 0; i < BM / 4; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                           a_dst0 + sbase + i * 4 * A_STRIDE * 8),
+                       "l"(a_src + (int64_t)(i * 4) * lda));
+        cp_async_mbar_arrive(full_bar);
+      }
+      // D tile.  batch q = pair rows (2q, 2q+1) of the stage for both determinants.
+      // lookups of one batch: ij (2 rows x 2 pairs), ta (4), tb (4 per determinant)
+      int ij[4], ta[4], tb0[4], tb1[4];
+      auto lookups = [&](int q, int (&ij_)[4], int (&ta_)[4], int (&t0_)[4], int (&t1_)[4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = kt * KSTEP + 2 * q + h;
+          const bool on = c < k_valid;
+          ij_[2 * h] = on ? ldg_int_g(pairs + 2 * (c_first + c)) : -1;
+          ij_[2 * h + 1] = on ? ldg_int_g(pairs + 2 * (c_first + c) + 1) : -1;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const bool on = ij_[h] >= 0;
+          ta_[h] = on ? ldg_int_g(ta_row + ij_[h]) : 0;
+          t0_[h] = (on && v0) ? ldg_int_g(mb0 + (int64_t)ij_[h] * lenb) : 0;
+          t1_[h] = (on && v1) ? ldg_int_g(mb1 + (int64_t)ij_[h] * lenb) : 0;
+        }
+      };
+      lookups(0, ij, ta, tb0, tb1);
+#pragma unroll 1
+      for (int q = 0; q < KSTEP / 2; ++q) {
+        // C elements of batch q: alpha sources (shared by both determinants' columns)
+        double2 va0[4], va1[4], vb0[4], vb1[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int64_t arow = (int64_t)(abs(ta[h]) - 1) * lenb;
+          va0[h] = ldg_c128_if_g(ta[h] != 0 && v0, ccol0 + arow);
+          va1[h] = ldg_c128_if_g(ta[h] != 0 && v1, ccol1 + arow);
+          vb0[h] = ldg_c128_if_g(tb0[h] != 0, crow + (abs(tb0[h]) - 1));
+          vb1[h] = ldg_c128_if_g(tb1[h] != 0, crow + (abs(tb1[h]) - 1));
+        }
+        // lookups of the next batch go out before this one is consumed
+        int nij[4], nta[4], nt0[4], nt1[4];
+        if (q + 1 < KSTEP / 2) lookups(q + 1, nij, nta, nt0, nt1);
+        auto sgn = [](int x) { return x < 0 ? -1.0 : 1.0; };
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k0 = 2 * h, k1 = 2 * h + 1;  // the (up to) two pairs of this row
+          const double re0 = (sgn(ta[k0]) * va0[k0].x + sgn(tb0[k0]) * vb0[k0].x) +
+                             (sgn(ta[k1]) * va0[k1].x + sgn(tb0[k1]) * vb0[k1].x);
+          const double im0 = (sgn(ta[k0]) * va0[k0].y + sgn(tb0[k0]) * vb0[k0].y) +
+                             (sgn(ta[k1]) * va0[k1].y + sgn(tb0[k1]) * vb0[k1].y);
+          const double re1 = (sgn(ta[k0]) * va1[k0].x + sgn(tb1[k0]) * vb1[k0].x) +
+                             (sgn(ta[k1]) * va1[k1].x + sgn(tb1[k1]) * vb1[k1].x);
+          const double im1 = (sgn(ta[k0]) * va1[k0].y + sgn(tb1[k0]) * vb1[k0].y) +
+                             (sgn(ta[k1]) * va1[k1].y + sgn(tb1[k1]) * vb1[k1].y);
+          const unsigned dst = b_dst0 + sbase + (2 * q + h) * B_STRIDE_R * 8;
+          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst), "d"(re0), "d"(im0)
+                       : "memory");
+          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst + 64 * 8), "d"(re1), "d"(im1)
+                       : "memory");
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          ij[h] = nij[h];
+          ta[h] = nta[h];
+          tb0[h] = nt0[h];
+          tb1[h] = nt1[h];
+        }
+      }
+      mbar_arrive(full_bar);
+      round_parity ^= 1;
+      first_round = false;
+      // advance this warp by STAGES stages
+      kt += STAGES;
+      while (kt >= nk) {
+        kt -= nk;
+        nb += gridDim.x;
+      }
+    }
+    asm volatile("cp.async.wait_all;\n" ::);
+    return;
+  }
+
+  // ============================= consumers =============================================
+  const int g = lane >> 2, tg = lane & 3;
+  const int wn0 = warp * (WN * 8);
+  const unsigned a_frag_off = (g * A_STRIDE + tg) * 8;
+  const unsigned b_frag_off = (A_TILE + tg * B_STRIDE_R + wn0 + g) * 8;
+  double acc[WM][WN][2];
+#pragma unroll
+  for (int i = 0; i < WM; ++i)
+#pragma unroll
+    for (int jn = 0; jn < WN; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+  int stage = 0;
+  unsigned parity = 0;
+  int mt_active = m_valid / 8;
+  mt_active = mt_active > WM ? WM : mt_active;
+  for (int64_t t = 0; t < my_tiles; ++t, nb += gridDim.x) {
+    for (int kt = 0; kt < nk; ++kt) {
+      mbar_wait(bar_full + stage * 8, parity);
+      const unsigned stage_u32 = smem_u32 + stage * STAGE_BYTES;
+      int kk_count = (k_valid - kt * KSTEP + 3) / 4;
+      kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
+      mma_stage<false, WM, WN, RAGGED>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off,
+                                       kk_count, mt_active);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + stage * 8);
+      if (++stage == STAGES) {
+        stage = 0;
+        parity ^= 1;
+      }
+    }
+    const int64_t n0 = nb * TILE_DETS;
+#pragma unroll
+    for (int mt = 0; mt < WM; ++mt) {
+      if (!RAGGED || mt < mt_active) {
+        const int kl = mt * 8 + g;
+        if (kl < nrows_out) {
+          double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
+#pragma unroll
+          for (int nt = 0; nt < WN; ++nt)
+            erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < WM; ++i)
+#pragma unroll
+      for (int jn = 0; jn < WN; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+  }
+}
+
+template <int WM>
+static int launch_fused_wm(const double *d_A, int lda, int a_col0, int c_first, int k_valid,
+                           const fqeb_graph *g, const fqeb_op *op, const double *d_coeff,
+                           int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde,
+                           int m_valid, cudaStream_t st) {
+  constexpr int BM = WM * 8;
+  const size_t smem = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES + 16 * STAGES;
+  const bool ragged = m_valid < BM;
+  auto kern = ragged ? k_sigma_fused<WM, true> : k_sigma_fused<WM, false>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_fused<WM, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_fused<WM, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  FQEB_REQUIRE(smem <= 227 * 1024, "fused sigma: shared memory budget exceeded");
+  const int tiles_per_row = pitch / 64;
+  const int64_t tiles = nrows * tiles_per_row;
+  int64_t grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, 384, smem, st>>>(
+      d_A, lda, a_col0, c_first, k_valid, op->d_pairs, g->d_amapT[0], g->d_amap[1],
+      g->norb * g->norb, (const double2 *)d_coeff, g->len[1], row0, pitch, tiles_per_row,
+      (double2 *)d_evec, lde, m_valid, op->np, tiles);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
+// fused gather + contraction of alpha rows [row0, row0+nrows) for pairs [ij0, ij1).
+// d_A: operand with the one-body term absorbed (see fused_operand in sigma.cu).
+int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
+                 int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde, int ij0,
+                 int ij1, cudaStream_t st) {
+  FQEB_REQUIRE(op->kind != FQEB_OP_COMPLEX, "fused sigma: real / imaginary operators only");
+  FQEB_REQUIRE((ij0 & 1) == 0 && ij0 < ij1 && ij1 <= op->np, "fused sigma: bad pair slice");
+  FQEB_REQUIRE(pitch % 64 == 0 && pitch >= g->len[1] && lde >= nrows * (int64_t)pitch,
+               "fused sigma: bad column layout");
+  const int m_valid = (int)round_up(op->np, 8);
+  const int k_valid = ij1 - ij0;
+  const GemmShape sh = pick_shape(false, m_valid);
+  FQEB_REQUIRE(sh.warps_m == 1 && m_valid <= sh.bm(), "fused sigma: pair space too large");
+#define FQEB_FUSED(WMV)                                                                        \
+  if (sh.wm == WMV)                                                                            \
+    return launch_fused_wm<WMV>(d_A, op->Kp, ij0, ij0, k_valid, g, op, d_coeff, row0, nrows,   \
+                                pitch, d_evec, lde, m_valid, st);
+  FQEB_FUSED(18)
+  FQEB_FUSED(17)
+  FQEB_FUSED(14)
+  FQEB_FUSED(13)
+  FQEB_FUSED(10)
+#undef FQEB_FUSED
+  set_error("fused sigma: no kernel for tile height %d", sh.wm);
+  return FQEB_ERR_INVALID;
+}
+
+// can the fused kernel cover this operator's row space with one block?
+bool fused_shape_ok(const fqeb_op *op) {
+  if (!op->has_h2 || op->kind == FQEB_OP_COMPLEX) return false;
+  const int m_valid = (int)round_up(op->np, 8);
+  const GemmShape sh = pick_shape(false, m_valid);
+  return sh.warps_m == 1 && m_valid <= sh.bm();
+}
+
 int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
                     int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st) {
   const int np = op->np;
@@ -807,12 +1103,87 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
       return fail(FQEB_ERR_CUDA);
     }
   }
+  // fused gather+contraction eligibility: single row block, real/imaginary class, and a
+  // one-body term that can be absorbed into the operand without leaving that class
+  // (and, in the compressed pair space, without breaking the i<->j symmetry)
+  op->fuse_ok = false;
+  if (op->has_h2 && fused_shape_ok(op)) {
+    const int part_zero = op->kind == FQEB_OP_IMAG ? 0 : 1;  // component of h1' that must vanish
+    bool ok = true;
+    for (int p = 0; p < npair && ok; ++p) ok = (h_h1p[2 * p + part_zero] == 0.0);
+    if (op->sym)
+      for (int i = 0; i < norb && ok; ++i)
+        for (int j = 0; j < i && ok; ++j)
+          ok = h_h1p[2 * (i * norb + j)] == h_h1p[2 * (j * norb + i)] &&
+               h_h1p[2 * (i * norb + j) + 1] == h_h1p[2 * (j * norb + i) + 1];
+    op->fuse_ok = ok;
+  }
+  if (op->fuse_ok) {
+    op->h_h1p = (double *)malloc(sizeof(double) * 2 * npair);
+    op->h_h2p = (double *)malloc(sizeof(double) * 2 * (size_t)npair * npair);
+    if (!op->h_h1p || !op->h_h2p) {
+      set_error("fqeb_op_create: host allocation failed");
+      return fail(FQEB_ERR_NOMEM);
+    }
+    memcpy(op->h_h1p, h_h1p, sizeof(double) * 2 * npair);
+    memcpy(op->h_h2p, h_h2p, sizeof(double) * 2 * (size_t)npair * npair);
+    op->fused_cache = new std::map<int, double *>();
+  }
   *out = op;
   return FQEB_OK;
 }
 
+namespace fqeb {
+// Operand of the fused kernel for a sector with n_elec electrons: the real/imaginary
+// part of h2' in the operator's pair space with the one-body term absorbed,
+//   A[c, d] += h1'[pair(c)] / n_elec   for every diagonal pair d = (k, k),
+// which is exact on a fixed-particle-number sector because sum_k E_kk = n_elec.
+// Built on first use and cached per n_elec.
+int fused_operand(const fqeb_op *op, int n_elec, const double **d_A) {
+  FQEB_REQUIRE(op->fuse_ok && n_elec > 0, "fused_operand: operator not fusable");
+  auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
+  auto it = cache->find(n_elec);
+  if (it != cache->end()) {
+    *d_A = it->second;
+    return FQEB_OK;
+  }
+  const int norb = op->norb, npair = norb * norb, np = op->np;
+  const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
+  auto pair_of = [&](int c) {
+    if (!op->sym) return c;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= c) ++i;
+    return i * norb + (c - i * (i + 1) / 2);
+  };
+  std::vector<double> a((size_t)op->Mp * op->Kp, 0.0);
+  for (int c = 0; c < np; ++c) {
+    const int ij = pair_of(c);
+    const double h1 = op->h_h1p[2 * ij + off] / (double)n_elec;
+    for (int d = 0; d < np; ++d) {
+      const int kl = pair_of(d);
+      double v = op->h_h2p[2 * ((size_t)ij * npair + kl) + off];
+      if (kl / norb == kl % norb) v += h1;
+      a[(size_t)c * op->Kp + d] = v;
+    }
+  }
+  double *dev = nullptr;
+  FQEB_CUDA(cudaMalloc(&dev, sizeof(double) * a.size()));
+  FQEB_CUDA(cudaMemcpy(dev, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice));
+  (*cache)[n_elec] = dev;
+  *d_A = dev;
+  return FQEB_OK;
+}
+}  // namespace fqeb
+
 extern "C" int fqeb_op_destroy(fqeb_op *op) {
   if (!op) return FQEB_OK;
+  if (op->fused_cache) {
+    auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
+    for (auto &kv : *cache) cudaFree(kv.second);
+    delete cache;
+  }
+  free(op->h_h1p);
+  free(op->h_h2p);
   if (op->d_A) cudaFree(op->d_A);
   if (op->d_h1) cudaFree(op->d_h1);
   if (op->d_pairs) cudaFree(op->d_pairs);

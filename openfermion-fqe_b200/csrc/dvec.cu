@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(kTB, 3)
 k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
              const int2 *__restrict__ clistT_a, const int2 *__restrict__ clist_b,
              const int32_t *__restrict__ rowmap, const double2 *__restrict__ evec, int64_t lde,
-             int64_t row0, int64_t nrows, int nbt, double2 z, double2 *__restrict__ out) {
+             int64_t pitch, int64_t row0, int64_t nrows, int nbt, double2 z,
+             double2 *__restrict__ out) {
   extern __shared__ int s_mem[];
   int *s_rowmap = s_mem;                                   // [npair]
   int2 *s_hits = reinterpret_cast<int2 *>(s_mem + ((npair + 1) & ~1));  // [lk_a]
@@ -235,7 +236,7 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
 #pragma unroll
     for (int u = 0; u < UA; ++u) {
       const int2 e = s_hits[h + u];
-      v[u] = ldg_c128(ecol + (int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * lenb);
+      v[u] = ldg_c128(ecol + (int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * pitch);
       sg[u] = e.y < 0 ? -1.0 : 1.0;
     }
 #pragma unroll
@@ -246,10 +247,10 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
   }
   for (; h < nhit; ++h) {
     const int2 e = s_hits[h];
-    axpy_sign(acc, e.y, ecol[(int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * lenb]);
+    axpy_sign(acc, e.y, ecol[(int64_t)e.x * lde + (int64_t)(abs(e.y) - 1) * pitch]);
   }
   if (in_chunk) {
-    const double2 *__restrict__ erow = evec + xr * lenb;
+    const double2 *__restrict__ erow = evec + xr * pitch;
     const int2 *__restrict__ cl = clist_b + b;
     int slot = 0;
     for (; slot + UB <= lk_b; slot += UB) {
@@ -321,8 +322,10 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
 }
 
 // rowmap == nullptr: identity (E row kl <-> pair kl)
-int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t row0,
-                      int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
+// pitch: distance (complex elements) between consecutive alpha rows inside an E row
+// (lenb for the plain layout, a multiple of 64 for the fused kernel's layout)
+int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t pitch,
+                      int64_t row0, int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
                       double *d_out, cudaStream_t st) {
   if (!d_rowmap) d_rowmap = g->d_rowmap_id;
   const int npair = g->norb * g->norb;
@@ -330,7 +333,8 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
   FQEB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= lena,
                "make_coeff: rows [%lld,+%lld) outside [0,%lld)", (long long)row0,
                (long long)nrows, (long long)lena);
-  FQEB_REQUIRE(lde >= nrows * lenb, "make_coeff: lde=%lld < nrows*lenb", (long long)lde);
+  FQEB_REQUIRE(pitch >= lenb && lde >= nrows * pitch, "make_coeff: lde=%lld < nrows*pitch",
+               (long long)lde);
   if (nrows == 0 || npair == 0) return FQEB_OK;
   const int nbt = (int)((lenb + kTB - 1) / kTB);
   const int64_t tiles = lena * nbt;
@@ -341,7 +345,8 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
                                    (int)smem));
   k_make_coeff<<<(unsigned)tiles, kTB, smem, st>>>(
       npair, lena, lenb, g->lk[0], g->lk[1], g->d_clistT[0], g->d_clist[1], d_rowmap,
-      (const double2 *)d_evec, lde, row0, nrows, nbt, make_double2(zr, zi), (double2 *)d_out);
+      (const double2 *)d_evec, lde, pitch, row0, nrows, nbt, make_double2(zr, zi),
+      (double2 *)d_out);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }
@@ -364,6 +369,6 @@ extern "C" int fqeb_make_coeff(const fqeb_graph *g, const double *d_evec, int64_
   int rc = fqeb::require_device();
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(g && d_evec && d_out, "fqeb_make_coeff: NULL argument");
-  return fqeb::launch_make_coeff(g, d_evec, lde, row0, nrows, nullptr, zr, zi, d_out,
+  return fqeb::launch_make_coeff(g, d_evec, lde, g->len[1], row0, nrows, nullptr, zr, zi, d_out,
                                  (cudaStream_t)stream);
 }

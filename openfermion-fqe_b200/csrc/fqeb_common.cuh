@@ -92,4 +92,9 @@ struct fqeb_op {
   int Mp, Kp;         // padded real dims of the FULL operator (whole pair space)
   double *d_h1;       // complex [norb*norb] (h1' / z), interleaved
   double zr, zi;      // global factor: 1 (real/complex) or i (imag)
+  // fused gather+contraction (dgemm.cu k_sigma_fused): usable when one CTA covers the
+  // whole row space and the one-body term can be folded into the operand
+  bool fuse_ok;
+  double *h_h1p, *h_h2p;   // host copies (complex, interleaved) for per-sector operands
+  void *fused_cache;       // std::map<int, double*>*: n_elec -> device operand with h1 absorbed
 };

@@ -26,9 +26,13 @@ namespace fqeb {
 int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
                      int64_t row0, int64_t nrows, int ij0, int ij1, const int32_t *d_pairs,
                      int np_eff, const double *d_h1, double *d_sig, cudaStream_t st);
-int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t row0,
-                      int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
+int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t pitch,
+                      int64_t row0, int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
                       double *d_out, cudaStream_t st);
+int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
+                 int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde, int ij0,
+                 int ij1, cudaStream_t st);
+int fused_operand(const fqeb_op *op, int n_elec, const double **d_A);
 int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
                     int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st);
 int dvec_rows_padded(const fqeb_op *op, int nij);
@@ -65,19 +69,40 @@ struct PhaseTimer {
 };
 
 struct ChunkLayout {
+  bool fused;         // D never materialised (k_sigma_fused)
+  int64_t pitch;      // complex elements between consecutive alpha rows inside a D/E row
   int64_t ldd;        // complex elements per D / E row
-  int64_t d_rows;     // rows of D (pair slice, padded)
+  int64_t d_rows;     // rows of D (pair slice, padded); 0 when fused
   int64_t e_rows;     // rows of E
   size_t d_bytes, e_bytes;
 };
 
+// The fused gather+contraction kernel (D never written to HBM) is OPT-IN: set
+// FQEB_FUSION=1.  It is parity-tested, but on B200 its four register-staged producer
+// warps cannot keep enough loads in flight per SM (measured at norb=16: 716 ms fused vs
+// 145 ms gather + 395 ms contraction), so the three-kernel path is the default.
+static bool use_fused(const fqeb_graph *g, const fqeb_op *op) {
+  const char *env = getenv("FQEB_FUSION");
+  const bool enabled = env && env[0] == '1';
+  return enabled && op->fuse_ok && (g->nele[0] + g->nele[1]) > 0;
+}
+
 static ChunkLayout layout_for(const fqeb_graph *g, const fqeb_op *op, int64_t rows, int ij0,
                               int ij1) {
   ChunkLayout L;
-  L.ldd = round_up(rows * g->len[1], fqeb_gemm_col_align());
-  L.d_rows = dvec_rows_padded(op, ij1 - ij0);
+  L.fused = use_fused(g, op);
   L.e_rows = round_up(op->np, 8);
-  L.d_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.d_rows * L.ldd, 256);
+  if (L.fused) {
+    L.pitch = round_up(g->len[1], 64);
+    L.ldd = rows * L.pitch;
+    L.d_rows = 0;
+    L.d_bytes = 0;
+  } else {
+    L.pitch = g->len[1];
+    L.ldd = round_up(rows * g->len[1], fqeb_gemm_col_align());
+    L.d_rows = dvec_rows_padded(op, ij1 - ij0);
+    L.d_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.d_rows * L.ldd, 256);
+  }
   L.e_bytes = (size_t)round_up(sizeof(double) * 2 * (size_t)L.e_rows * L.ldd, 256);
   return L;
 }
@@ -153,6 +178,27 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   double *d_dvec = (double *)d_workspace;
   double *d_evec = (double *)((char *)d_workspace + L.d_bytes);
   const int nij = ij1 - ij0;
+  if (L.fused) {
+    const double *d_A = nullptr;
+    rc = fused_operand(op, g->nele[0] + g->nele[1], &d_A);
+    if (rc != FQEB_OK) return rc;
+    double *d_e = (double *)d_workspace;
+    for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
+      const int64_t nr = (row1 - a0) < rows_chunk ? (row1 - a0) : rows_chunk;
+      {
+        PhaseTimer t(1, st);
+        rc = launch_fused(g, op, d_A, d_coeff, a0, nr, (int)L.pitch, d_e, L.ldd, ij0, ij1, st);
+      }
+      if (rc != FQEB_OK) return rc;
+      {
+        PhaseTimer t(2, st);
+        rc = launch_make_coeff(g, d_e, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi,
+                               d_sigma, st);
+      }
+      if (rc != FQEB_OK) return rc;
+    }
+    return FQEB_OK;
+  }
   const int zrows = dvec_rows_zeroed(op, nij);
   if (zrows > nij) {
     // the k-padding rows of D that a partial k4 step reads must be exact zeros
@@ -175,8 +221,8 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
     if (rc != FQEB_OK) return rc;
     {
       PhaseTimer t(2, st);
-      rc = launch_make_coeff(g, d_evec, L.ldd, a0, nr, op->d_rowmap, op->zr, op->zi, d_sigma,
-                             st);
+      rc = launch_make_coeff(g, d_evec, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi,
+                             d_sigma, st);
     }
     if (rc != FQEB_OK) return rc;
   }
