@@ -13,7 +13,7 @@
 // HBM roofline: 32 bytes per determinant (read + write C); strings and per-string
 // terms (24 B per beta string) are re-read per alpha row from L2.  One CTA owns an
 // alpha row at a time (grid-strided), threads sweep the beta index with 16-byte
-// coalesced accesses; the norb-long S_a / P_a vector lives in shared memory.
+// coalesced accesses; the cross term comes from byte-indexed shared-memory tables.
 #include "fqeb_common.cuh"
 
 namespace fqeb {
@@ -59,49 +59,88 @@ __global__ void k_dc_string_terms(int norb, int64_t len, const uint64_t *__restr
   out[x] = acc;
 }
 
+// One CTA owns an alpha row at a time.  The alpha-beta cross term of element (a, b) is
+// sum (apply) / product (evolve) over the occupied orbitals j of b of cross_a[j]; it is
+// evaluated with byte-indexed lookup tables built once per row in shared memory
+// (tab[k][m] = combination of cross_a[8k + bit] over the bits of m), so an element costs
+// ceil(norb/8) shared-memory lookups instead of a loop over its nbeta set bits.
 template <bool EVOLVE>
 __global__ void __launch_bounds__(256)
 k_dc_main(int norb, int64_t lena, int64_t lenb, const uint64_t *__restrict__ astr,
           const uint64_t *__restrict__ bstr, const double2 *__restrict__ v,
           const double2 *__restrict__ aterm, const double2 *__restrict__ bterm,
           double2 *__restrict__ coeff) {
+  extern __shared__ double2 s_tab[];  // [nbytes][256]
   __shared__ double2 cross[64];
+  const int nbytes = (norb + 7) / 8;
+  const double2 ident = EVOLVE ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
   for (int64_t a = blockIdx.x; a < lena; a += gridDim.x) {
     const uint64_t sa = astr[a];
-    if (threadIdx.x < norb) {
+    if (threadIdx.x < 64) {
       const int j = threadIdx.x;
-      double2 acc = EVOLVE ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
-      uint64_t si = sa;
-      while (si) {
-        const int i = __ffsll((long long)si) - 1;
-        si &= si - 1;
-        if (EVOLVE) {
-          acc = zmul(acc, v[i * norb + j]);
-        } else {
-          acc = zadd(acc, v[i * norb + j]);
-          acc = zadd(acc, v[j * norb + i]);
+      double2 acc = ident;
+      if (j < norb) {
+        uint64_t si = sa;
+        while (si) {
+          const int i = __ffsll((long long)si) - 1;
+          si &= si - 1;
+          if (EVOLVE) {
+            acc = zmul(acc, v[i * norb + j]);
+          } else {
+            acc = zadd(acc, v[i * norb + j]);
+            acc = zadd(acc, v[j * norb + i]);
+          }
         }
       }
       cross[j] = acc;
     }
     __syncthreads();
+    for (int e = threadIdx.x; e < nbytes * 256; e += blockDim.x) {
+      const int k = e >> 8;
+      unsigned m = e & 255;
+      double2 acc = ident;
+      while (m) {
+        const int bit = __ffs((int)m) - 1;
+        m &= m - 1;
+        const double2 cj = cross[8 * k + bit];
+        acc = EVOLVE ? zmul(acc, cj) : zadd(acc, cj);
+      }
+      s_tab[e] = acc;
+    }
+    __syncthreads();
     const double2 at = aterm[a];
-    double2 *row = coeff + a * lenb;
-    for (int64_t b = threadIdx.x; b < lenb; b += blockDim.x) {
-      uint64_t sb = bstr[b];
-      double2 x = EVOLVE ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
-      while (sb) {
-        const int j = __ffsll((long long)sb) - 1;
-        sb &= sb - 1;
-        x = EVOLVE ? zmul(x, cross[j]) : zadd(x, cross[j]);
+    double2 *__restrict__ row = coeff + a * lenb;
+    // four elements per trip: all loads first (memory-level parallelism), then math + stores
+    constexpr int U = 4;
+    for (int64_t b0 = threadIdx.x; b0 < lenb; b0 += (int64_t)U * blockDim.x) {
+      uint64_t sb[U];
+      double2 bt[U], cv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = b0 + (int64_t)u * blockDim.x;
+        const bool on = b < lenb;
+        sb[u] = on ? __ldg(bstr + b) : 0ull;
+        bt[u] = on ? __ldg(bterm + b) : ident;
+        cv[u] = on ? row[b] : make_double2(0.0, 0.0);
       }
-      double2 f;
-      if (EVOLVE) {
-        f = zmul(zmul(zmul(x, x), bterm[b]), at);
-      } else {
-        f = zadd(zadd(x, bterm[b]), at);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = b0 + (int64_t)u * blockDim.x;
+        double2 x = ident;
+        uint64_t bits = sb[u];
+        for (int k = 0; k < nbytes; ++k) {
+          const double2 tk = s_tab[k * 256 + (int)(bits & 255)];
+          bits >>= 8;
+          x = EVOLVE ? zmul(x, tk) : zadd(x, tk);
+        }
+        double2 f;
+        if (EVOLVE) {
+          f = zmul(zmul(zmul(x, x), bt[u]), at);
+        } else {
+          f = zadd(zadd(x, bt[u]), at);
+        }
+        if (b < lenb) row[b] = zmul(cv[u], f);
       }
-      row[b] = zmul(row[b], f);
     }
     __syncthreads();
   }
@@ -142,7 +181,8 @@ static int dc_run(const fqeb_graph *g, const double *h_diag, const double *h_arr
   const double2 *bterm = (const double2 *)g->d_sterm[g->shared_spin ? 0 : 1];
   int64_t grid = (int64_t)sm_count() * 8;
   if (grid > g->len[0]) grid = g->len[0];
-  k_dc_main<EVOLVE><<<(unsigned)grid, 256, 0, st>>>(norb, g->len[0], g->len[1], g->d_str[0],
+  const size_t tab_bytes = sizeof(double2) * 256 * (size_t)((norb + 7) / 8);
+  k_dc_main<EVOLVE><<<(unsigned)grid, 256, tab_bytes, st>>>(norb, g->len[0], g->len[1], g->d_str[0],
                                                     g->d_str[1], use_v, aterm, bterm,
                                                     (double2 *)d_coeff);
   FQEB_CHECK_LAUNCH();

@@ -48,7 +48,8 @@
 namespace fqeb {
 
 constexpr int BNR = 128;      // real columns per CTA tile
-constexpr int KSTEP = 16;     // real k per pipeline stage
+constexpr int KSTEP = 16;     // real k per pipeline stage (default geometry)
+constexpr int KSTEP_MAX = 32; // largest k-step of any instantiated pipeline (padding)
 constexpr int STAGES = 4;
 constexpr int A_STRIDE = KSTEP + 4;   // doubles
 constexpr int B_STRIDE_R = BNR + 4;   // REAL: [16][132]
@@ -112,10 +113,11 @@ __device__ __forceinline__ double lds_f64(unsigned base) {
 
 // All DMMAs of one pipeline stage for one warp.  a_base / b_base: shared-memory byte
 // addresses of this lane's first A / B fragment element in the stage.
-template <bool CPLX, int WM, int WN, bool RAGGED>
+template <bool CPLX, int WM, int WN, bool RAGGED, int KS = KSTEP>
 __device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], unsigned a_base,
                                           unsigned b_base, int kk_count, int mt_active) {
-  static_for<0, KSTEP / 4>([&](auto kk_c) {
+  constexpr int A_STRIDE = KS + 4;  // shadows the KSTEP=16 constant: row stride of this KS
+  static_for<0, KS / 4>([&](auto kk_c) {
     constexpr int kk = decltype(kk_c)::value;
     if (kk < kk_count) {
       double bf[WN];
@@ -355,11 +357,15 @@ __device__ __forceinline__ void cp_async_mbar_arrive(unsigned addr) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
 }
 
-template <bool CPLX, int WARPS_M, int WM, int WN, bool RAGGED>
+template <bool CPLX, int WARPS_M, int WM, int WN, bool RAGGED, int KS, int NST>
 __global__ void __launch_bounds__(320, 1)
 k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
            int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out,
            int k_valid, int nmb, int64_t ntiles) {
+  // pipeline geometry of this instantiation (shadow the KSTEP=16 / STAGES=4 constants)
+  constexpr int KSTEP = KS, STAGES = NST;
+  constexpr int A_STRIDE = KS + 4;
+  constexpr int B_TILE = KS * B_STRIDE_R;  // == (KS/2) * B_STRIDE_C
   constexpr int BM = WARPS_M * WM * 8;
   constexpr int WARPS_N = 8 / WARPS_M;
   static_assert(WARPS_N * WN * 8 == BNR, "warp layout must span 128 columns");
@@ -476,7 +482,7 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
     const unsigned stage_u32 = smem_u32 + stage * STAGE_BYTES;
     int kk_count = (k_valid - kt * KSTEP + 3) / 4;
     kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
-    mma_stage<CPLX, WM, WN, RAGGED>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off, kk_count,
+    mma_stage<CPLX, WM, WN, RAGGED, KS>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off, kk_count,
                                     mt_active);
     // release the slot: every lane's fragment loads have been consumed by its DMMAs
     __syncwarp();
@@ -542,28 +548,63 @@ struct GemmShape {
 };
 static const GemmShape kShapes[] = {{2, 8}, {1, 18}, {1, 17}, {1, 14}, {1, 13}, {1, 10}};
 
+template <bool CPLX, int WARPS_M, int WM, int WN, int KS, int NST>
+static int launch_ws(const fqeb_op *op, int a_col0, const double *d_dvec, int64_t ldd,
+                     double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
+                     cudaStream_t st) {
+  constexpr int BM = WARPS_M * WM * 8;
+  constexpr size_t SMEM =
+      sizeof(double) * (size_t)(BM * (KS + 4) + KS * B_STRIDE_R) * NST + 16 * NST;
+  static_assert(SMEM <= 227 * 1024, "pipeline does not fit in shared memory");
+  const bool ragged = (m_valid % BM) != 0;
+  auto kern = ragged ? k_dgemm_ws<CPLX, WARPS_M, WM, WN, true, KS, NST>
+                     : k_dgemm_ws<CPLX, WARPS_M, WM, WN, false, KS, NST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, true, KS, NST>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, false, KS, NST>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  const int nmb = (m_valid + BM - 1) / BM;
+  const int64_t tiles = nnb * nmb;
+  int64_t grid = sm_count();
+  if (grid > nmb) grid -= grid % nmb;
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, 320, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+                                          (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
+                                          tiles);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
 template <bool CPLX, int WARPS_M, int WM, int WN>
 static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int64_t ldd,
                         double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
                         cudaStream_t st) {
   constexpr int BM = WARPS_M * WM * 8;
-  // + 2*STAGES mbarriers (used by the warp-specialised variant only)
-  constexpr size_t SMEM =
-      sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES + 16 * STAGES;
-  // FQEB_GEMM_WS=0 selects the classic (all warps load and compute) variant
+  // FQEB_GEMM_WS=0 selects the classic (all warps load and compute) variant;
+  // FQEB_GEMM_PIPE picks the warp-specialised pipeline geometry: 1 = k-step 32 x 3 stages
+  // (default: fewest stage hand-overs per DMMA; 31.8 / 35.0 TFLOP/s at norb=16),
+  // 0 = k-step 16 x 4 stages (31.0 / 33.6), 2 = k-step 16 x 5 stages (30.8 / 33.3)
   static const bool ws = !(getenv("FQEB_GEMM_WS") && getenv("FQEB_GEMM_WS")[0] == '0');
-  static bool attr_set = false;
-  // RAGGED: the last row block is partial, per-tile predicates on the row tiles
+  static const int pipe = getenv("FQEB_GEMM_PIPE") ? atoi(getenv("FQEB_GEMM_PIPE")) : 1;
+  if (ws) {
+    if (pipe == 1)
+      return launch_ws<CPLX, WARPS_M, WM, WN, 32, 3>(op, a_col0, d_dvec, ldd, d_evec, lde,
+                                                     m_valid, k_valid, nnb, st);
+    if (pipe == 2)
+      return launch_ws<CPLX, WARPS_M, WM, WN, 16, 5>(op, a_col0, d_dvec, ldd, d_evec, lde,
+                                                     m_valid, k_valid, nnb, st);
+    return launch_ws<CPLX, WARPS_M, WM, WN, 16, 4>(op, a_col0, d_dvec, ldd, d_evec, lde, m_valid,
+                                                   k_valid, nnb, st);
+  }
+  constexpr size_t SMEM = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES;
   const bool ragged = (m_valid % BM) != 0;
-  auto kern = ws ? (ragged ? k_dgemm_ws<CPLX, WARPS_M, WM, WN, true>
-                           : k_dgemm_ws<CPLX, WARPS_M, WM, WN, false>)
-                 : (ragged ? k_dgemm<CPLX, WARPS_M, WM, WN, true>
-                           : k_dgemm<CPLX, WARPS_M, WM, WN, false>);
+  auto kern = ragged ? k_dgemm<CPLX, WARPS_M, WM, WN, true> : k_dgemm<CPLX, WARPS_M, WM, WN, false>;
+  static bool attr_set = false;
   if (!attr_set) {
-    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, false>,
@@ -583,7 +624,7 @@ static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int
     if (grid > tiles) grid = tiles;
   }
   FQEB_REQUIRE(grid < (1ll << 31), "contract: too many tiles for one launch");
-  kern<<<(unsigned)grid, ws ? 320 : 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+  kern<<<(unsigned)grid, 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
                                           (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
                                           tiles);
   FQEB_CHECK_LAUNCH();
@@ -907,7 +948,8 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
   const int k_valid = cplx ? 2 * nij : nij;
   const int nk = (k_valid + KSTEP - 1) / KSTEP;
   const int a_col0 = cplx ? 2 * ij0 : ij0;
-  FQEB_REQUIRE(a_col0 + nk * KSTEP <= op->Kp, "contract: operator padding too small");
+  FQEB_REQUIRE(a_col0 + round_up(k_valid, KSTEP_MAX) <= op->Kp,
+               "contract: operator padding too small");
   const int m_valid = cplx ? 2 * (int)round_up(np, 8) : (int)round_up(np, 8);
   const int64_t cols_pad = round_up(ncols, COL_ALIGN);
   const int64_t nnb = cols_pad / (cplx ? BNR : BNR / 2);
@@ -940,7 +982,7 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
 // rows of D a caller must allocate for a slice of nij pairs (whole pipeline stages) ...
 int dvec_rows_padded(const fqeb_op *op, int nij) {
   const bool cplx = op->kind == FQEB_OP_COMPLEX;
-  return (int)round_up(nij, cplx ? KSTEP / 2 : KSTEP);
+  return (int)round_up(nij, cplx ? KSTEP_MAX / 2 : KSTEP_MAX);
 }
 // ... of which rows [nij, this) are read by a partial k4 step and must be zero
 int dvec_rows_zeroed(const fqeb_op *op, int nij) {
@@ -1075,7 +1117,7 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
     if (op->kind == FQEB_OP_COMPLEX) {
       const int np8 = (int)round_up(np, 8);
       op->Mp = (int)round_up(2 * np8, MAX_BM) + MAX_BM;
-      op->Kp = (int)round_up(2 * np, KSTEP) + KSTEP;  // slack for ragged slices
+      op->Kp = (int)round_up(2 * np, KSTEP_MAX) + KSTEP_MAX;  // slack for ragged slices
       a.assign((size_t)op->Mp * op->Kp, 0.0);
       for (int c = 0; c < np; ++c) {
         const int rre = (c / 8) * 16 + (c % 8), rim = rre + 8;
@@ -1090,7 +1132,7 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
     } else {
       const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
       op->Mp = (int)round_up(round_up(np, 8), MAX_BM) + MAX_BM;
-      op->Kp = (int)round_up(np, KSTEP) + KSTEP;
+      op->Kp = (int)round_up(np, KSTEP_MAX) + KSTEP_MAX;
       a.assign((size_t)op->Mp * op->Kp, 0.0);
       for (int c = 0; c < np; ++c)
         for (int d = 0; d < np; ++d) a[(size_t)c * op->Kp + d] = elem(c, d, off);

@@ -105,20 +105,28 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
   const int32_t *__restrict__ mb = amap_b + b;
   double2 *__restrict__ dout = dvec + r * lenb + b;
   double2 acc = make_double2(0.0, 0.0);
-  // Two pair-space rows per trip, in three phases so that the four beta-map loads and
-  // then the (up to) eight C loads are all in flight together.
+  // Two pair-space rows per trip.  Software-pipelined: the beta-map entries of trip n+1
+  // are requested before the C elements of trip n are consumed, so a trip costs one
+  // global-memory round trip instead of two dependent ones.
+  // (absent pairs are masked, which keeps the batch branch-free)
+  auto load_tb = [&](int c, int4 &j0, int4 &j1, int &t00, int &t01, int &t10, int &t11) {
+    const bool one = (c < c1), two = (c + 1 < c1);
+    j0 = one ? s_info[c - c0] : make_int4(0, -1, 0, 0);
+    j1 = two ? s_info[c + 1 - c0] : make_int4(0, -1, 0, 0);
+    t00 = one ? ldg_int(mb + (int64_t)j0.x * lenb) : 0;
+    t01 = (j0.y >= 0) ? ldg_int(mb + (int64_t)j0.y * lenb) : 0;
+    t10 = two ? ldg_int(mb + (int64_t)j1.x * lenb) : 0;
+    t11 = (j1.y >= 0) ? ldg_int(mb + (int64_t)j1.y * lenb) : 0;
+    if (!one) j0.z = j0.w = 0;
+    if (!two) j1.z = j1.w = 0;
+  };
+  int4 i0, i1;
+  int tb00, tb01, tb10, tb11;
+  load_tb(c0, i0, i1, tb00, tb01, tb10, tb11);
   for (int c = c0; c < c1; c += 2) {
     const bool two = (c + 1 < c1);
-    const int4 i0 = s_info[c - c0];
-    const int4 i1 = two ? s_info[c + 1 - c0] : make_int4(0, -1, 0, 0);
-    // phase 1: beta map entries
-    // (absent pairs read entry 0 of the map and are masked: keeps the batch branch-free)
-    const int tb00 = ldg_int(mb + (int64_t)i0.x * lenb);
-    const int tb01 = (i0.y >= 0) ? ldg_int(mb + (int64_t)i0.y * lenb) : 0;
-    const int tb10 = two ? ldg_int(mb + (int64_t)i1.x * lenb) : 0;
-    const int tb11 = (i1.y >= 0) ? ldg_int(mb + (int64_t)i1.y * lenb) : 0;
-    const int ta00 = i0.z, ta01 = i0.w, ta10 = two ? i1.z : 0, ta11 = i1.w;
-    // phase 2: C elements (predicated loads)
+    const int ta00 = i0.z, ta01 = i0.w, ta10 = i1.z, ta11 = i1.w;
+    // C elements of this trip (predicated loads)
     const double2 va00 = ldg_c128_if(ta00 != 0, ccol + (int64_t)(abs(ta00) - 1) * lenb);
     const double2 va01 = ldg_c128_if(ta01 != 0, ccol + (int64_t)(abs(ta01) - 1) * lenb);
     const double2 va10 = ldg_c128_if(ta10 != 0, ccol + (int64_t)(abs(ta10) - 1) * lenb);
@@ -127,6 +135,10 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
     const double2 vb01 = ldg_c128_if(tb01 != 0, crow + (abs(tb01) - 1));
     const double2 vb10 = ldg_c128_if(tb10 != 0, crow + (abs(tb10) - 1));
     const double2 vb11 = ldg_c128_if(tb11 != 0, crow + (abs(tb11) - 1));
+    // map entries of the next trip
+    int4 n0, n1;
+    int nb00, nb01, nb10, nb11;
+    load_tb(c + 2, n0, n1, nb00, nb01, nb10, nb11);
     // phase 3: signed sums (multiplying by +-1.0 is exact)
     auto sgn = [](int t) { return t < 0 ? -1.0 : 1.0; };
     const double2 d00 = make_double2(sgn(ta00) * va00.x + sgn(tb00) * vb00.x,
@@ -161,6 +173,12 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
         }
       }
     }
+    i0 = n0;
+    i1 = n1;
+    tb00 = nb00;
+    tb01 = nb01;
+    tb10 = nb10;
+    tb11 = nb11;
   }
   if (H1) {
     double2 s = sig[a * lenb + b];

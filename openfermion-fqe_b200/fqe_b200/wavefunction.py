@@ -337,6 +337,7 @@ class Wavefunction:
 
         if numpy.abs(hamil.e_0()) > 1.0e-15:
             final_wfn.scale(numpy.exp(-1.j * time * hamil.e_0()))
+        self.last_expansion_order = getattr(work_wfn, "last_expansion_order", 0)
         return final_wfn
 
     def _evolve_diagonal_coulomb_inplace(self, diag: numpy.ndarray,

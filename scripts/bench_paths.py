@@ -1,0 +1,88 @@
+"""Secondary measurements for the other BASELINE.json configs (not the bench.py contract):
+  config 2: norb=14 sigma apply + Taylor time_evolve on one GPU
+  config 3: norb=16 DiagonalCoulomb apply / evolve (HBM-bound: 32*L^2 bytes per pass)
+  BLAS-1 : axpy / scale / norm / fused axpy+norm at norb=16
+Prints one JSON object; CUDA-event timing, 3 warm-ups, inputs larger than L2."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "openfermion-fqe_b200"))
+import numpy as np
+import torch
+import fqe_b200 as fqe
+from fqe_b200 import synth
+
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+HBM = peaks["hbm_gbs"]
+
+
+def timed(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+out = {"hbm_peak_GBps": HBM}
+
+# ---- config 3: diagonal Coulomb at norb=16 ------------------------------------------------
+norb, n, sz = 16, 16, 0
+na, nb, la, lb = synth.sector_dims(n, sz, norb)
+wfn = fqe.Wavefunction([[n, sz, norb]])
+gen = torch.Generator(device="cuda").manual_seed(7)
+wfn.set_wfn(strategy="from_data", raw_data={(n, sz): torch.view_as_complex(
+    torch.randn((la, lb, 2), dtype=torch.float64, device="cuda", generator=gen))})
+wfn.normalize()
+sec = wfn.sector((n, sz))
+vij = synth.diagonal_coulomb_matrix(norb, 3)
+diag = np.zeros(norb)
+nbytes = 32.0 * la * lb
+ms = timed(lambda: sec.apply_diagonal_coulomb(diag, vij, inplace=True))
+out["dc_apply_norb16"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / HBM}
+ms = timed(lambda: sec.evolve_diagonal_coulomb(-0.1j * diag, -0.1j * vij, inplace=True))
+out["dc_evolve_norb16"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / HBM}
+other = sec.empty_copy(zero=False)
+other.coeff.copy_(sec.coeff)
+ms = timed(lambda: sec.ax_plus_y(1e-6 + 1e-6j, other))
+out["zaxpy_norb16"] = {"ms": ms, "GBps": 48.0 * la * lb / ms / 1e6}
+ms = timed(lambda: sec.scale(1.0 + 1e-9j))
+out["zscal_norb16"] = {"ms": ms, "GBps": nbytes / ms / 1e6}
+ms = timed(lambda: sec.norm())
+out["znorm_norb16"] = {"ms": ms, "GBps": 16.0 * la * lb / ms / 1e6}
+ms = timed(lambda: sec.axpy_norm(1e-6, other))
+out["axpy_norm_norb16"] = {"ms": ms, "GBps": 48.0 * la * lb / ms / 1e6}
+del wfn, sec, other
+torch.cuda.empty_cache()
+
+# ---- config 2: norb=14 sigma + Taylor time_evolve -----------------------------------------
+norb, n, sz = 14, 14, 0
+na, nb, la, lb = synth.sector_dims(n, sz, norb)
+h1, h2 = synth.integrals(norb, "real8", scale=0.05)
+ham = fqe.get_restricted_hamiltonian((h1, h2), e_0=-1.0)
+wfn = fqe.Wavefunction([[n, sz, norb]])
+wfn.set_wfn(strategy="from_data", raw_data={(n, sz): synth.state(la, lb, seed=14)})
+ms = timed(lambda: wfn.apply(ham), reps=3, warm=2)
+out["sigma_norb14_real8"] = {"ms": ms, "sigma_per_s": 1e3 / ms}
+# |H| from a few power iterations, then t = 0.5/|H| so Taylor converges well under 30 terms
+x = wfn
+for _ in range(3):
+    y = x.apply(ham)
+    hn = y.norm()
+    y.scale(1.0 / hn)
+    x = y
+t = 0.5 / hn
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+ev = wfn.time_evolve(t, ham)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+out["time_evolve_norb14"] = {"t": t, "H_norm_est": hn, "taylor_terms": wfn.last_expansion_order
+                             if hasattr(wfn, "last_expansion_order") else None,
+                             "seconds": dt, "norm_after": ev.norm()}
+print(json.dumps(out))
