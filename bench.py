@@ -368,6 +368,16 @@ def run_b200(args):
 
     flop, achieved, phases, share = summarise(main)
     value = args.steps / (main["ms_total"] * 1e-3)
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of the
+    # same workload (profiles/r01_traffic.json); only quoted for the configuration it was
+    # taken on (norb=16, real pair-symmetric operator, one GPU)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.norb == 16 and world == 1 and main["op_sym"] and main["op_kind"] != L.OP_COMPLEX:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -391,7 +401,9 @@ def run_b200(args):
         "roofline": {
             "bound": "tensor", "kernel": "k_dgemm (FP64 DMMA contraction)",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+            "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+            "traffic_unit": "DRAM bytes per contraction launch (ncu), see profiles/r01_traffic.json",
+            "launches_per_step": main["phase_launches"][1] // max(args.steps, 1),
             "flops_per_step_per_rank": flop,
             "flop_model": ("%d*P^2*L^2 with P=%d pairs (%s; %s)" % (
                 8 if main["op_kind"] == L.OP_COMPLEX else 4, main["op_npair"],

@@ -288,8 +288,8 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
               double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt) {
-                erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
-                erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
+                __stcs(erow + nt * 8, make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]));
+                __stcs(erow + nt * 8 + 1, make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]));
               }
             }
           }
@@ -303,7 +303,7 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
               double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt)
-                erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                __stcs(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
             }
           }
         }
@@ -405,9 +405,13 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
     constexpr int B_STRIDE = CPLX ? B_STRIDE_C : B_STRIDE_R;
     constexpr int B_SUB = B_CHUNKS / 32;        // lane-strided pieces per B row
     constexpr int B_ROWS_STAGE = CPLX ? KSTEP / 2 : KSTEP;
-    // A: chunk id = lane + 32*i -> row = 4*i + lane/8, 16-byte column = lane%8
-    const unsigned a_dst0 = smem_u32 + ((lane >> 3) * A_STRIDE + (lane & 7) * 2) * 8;
-    const double *a_thr = A + a_col0 + (int64_t)(lane >> 3) * lda + (lane & 7) * 2;
+    // A: a row of the tile is KSTEP/2 16-byte chunks; one pass of the warp covers
+    // A_RPP = 32 / (KSTEP/2) rows: chunk id = lane + 32*i -> row = A_RPP*i + lane/A_CPR
+    constexpr int A_CPR = KSTEP / 2;      // chunks per row
+    constexpr int A_RPP = 32 / A_CPR;     // rows per pass
+    static_assert(32 % A_CPR == 0 && BM % A_RPP == 0, "operand tile / warp mismatch");
+    const unsigned a_dst0 = smem_u32 + ((lane / A_CPR) * A_STRIDE + (lane % A_CPR) * 2) * 8;
+    const double *a_thr = A + a_col0 + (int64_t)(lane / A_CPR) * lda + (lane % A_CPR) * 2;
     // B: piece j of row r -> chunk lane + 32*j
     const unsigned b_dst0 = smem_u32 + (A_TILE + lane * 2) * 8;
     const double2 *b_thr = B + lane;
@@ -421,10 +425,10 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
       const unsigned sbase = stage * STAGE_BYTES;
       if (loads_a) {
 #pragma unroll 8
-        for (int i = 0; i < BM / 4; ++i)
+        for (int i = 0; i < BM / A_RPP; ++i)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                           a_dst0 + sbase + i * 4 * A_STRIDE * 8),
-                       "l"(a_src + (int64_t)(i * 4) * lda));
+                           a_dst0 + sbase + i * A_RPP * A_STRIDE * 8),
+                       "l"(a_src + (int64_t)(i * A_RPP) * lda));
       } else {
 #pragma unroll 8
         for (int i = 0; i < B_ROWS_STAGE * B_SUB; ++i) {
@@ -503,8 +507,8 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
               double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt) {
-                erow[nt * 8] = make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]);
-                erow[nt * 8 + 1] = make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]);
+                __stcs(erow + nt * 8, make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]));
+                __stcs(erow + nt * 8 + 1, make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]));
               }
             }
           }
@@ -518,7 +522,7 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
               double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt)
-                erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                __stcs(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
             }
           }
         }
@@ -856,7 +860,7 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
           double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
           for (int nt = 0; nt < WN; ++nt)
-            erow[nt * 4] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            __stcs(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
         }
       }
     }

@@ -150,8 +150,11 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
     const double2 d11 = make_double2(sgn(ta11) * va11.x + sgn(tb11) * vb11.x,
                                      sgn(ta11) * va11.y + sgn(tb11) * vb11.y);
     if (WRITE_D) {
-      dout[(int64_t)(c - c0) * ldd] = make_double2(d00.x + d01.x, d00.y + d01.y);
-      if (two) dout[(int64_t)(c + 1 - c0) * ldd] = make_double2(d10.x + d11.x, d10.y + d11.y);
+      // streaming stores: D is far larger than L2 and is read back only by the next kernel;
+      // evict-first keeps C rows and the map tables resident instead
+      __stcs(dout + (int64_t)(c - c0) * ldd, make_double2(d00.x + d01.x, d00.y + d01.y));
+      if (two)
+        __stcs(dout + (int64_t)(c + 1 - c0) * ldd, make_double2(d10.x + d11.x, d10.y + d11.y));
     }
     if (H1) {
       const double2 h00 = h1[i0.x];
