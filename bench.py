@@ -212,7 +212,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
     """Time K sigma builds (device-resident) and, optionally, K end-to-end builds."""
     import ctypes
     from fqe_b200 import synth
-    from fqe_b200.distributed import shard_plan, sharded_apply
+    from fqe_b200.distributed import shard_plan, sharded_apply, sharded_apply_host
     from fqe_b200.fqe_data import DenseOperator
 
     norb = args.norb
@@ -281,14 +281,22 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         host_out = torch.empty((la, lb), dtype=torch.complex128).pin_memory()
 
         def e2e_step():
-            sector.coeff.copy_(host_c, non_blocking=True)          # H2D of this step's input
             ham = fqe.get_restricted_hamiltonian((h1, h2))
             op_i = wfn._dense_operator(ham.tensors())                # operator preparation
-            out = sharded_apply(sector, op_i, args.shard)
-            host_out.copy_(out, non_blocking=True)                   # D2H of the result
+            # H2D of this step's input (each rank its row slice, exchanged over NVLink),
+            # sharded sigma + allreduce, D2H of the result (each rank its row slice)
+            sharded_apply_host(sector, op_i, host_c, host_out, args.shard)
             torch.cuda.synchronize()
 
         e2e_step()
+        if args.verify:
+            ref = sharded_apply(sector, op, args.shard)
+            r0, r1 = (0, la) if world == 1 else __import__(
+                "fqe_b200.distributed", fromlist=["split_even"]).split_even(la, world)[rank]
+            got = host_out[r0:r1].cuda()
+            result["e2e_verify"] = float((torch.linalg.norm(got - ref[r0:r1]) /
+                                          torch.linalg.norm(ref[r0:r1])).item())
+            del ref, got
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -299,7 +307,8 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         result["e2e_s"] = float(t.item())
-        result["h2d"] = host_c.numel() * 16 + h1.nbytes + h2.nbytes
+        # bytes over PCIe per step, summed over all ranks
+        result["h2d"] = host_c.numel() * 16 + world * (h1.nbytes + h2.nbytes)
         result["d2h"] = host_out.numel() * 16
     return result
 
@@ -394,7 +403,7 @@ def run_b200(args):
                 main["op_kind"]] + (", pair-symmetric" if main["op_sym"] else ""),
         },
         "gpu_launches": main["launches"],
-        "verify_rel_err": main["verify"],
+        "verify_rel_err": main["verify"], "e2e_verify_rel_err": main.get("e2e_verify"),
         "clocks": main["clocks"],
         "e2e": {"value": args.steps / main["e2e_s"], "unit": "sigma/s",
                 "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},

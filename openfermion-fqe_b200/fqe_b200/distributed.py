@@ -66,3 +66,31 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
                              op.npair)
     part = sector.apply_operator(op, row_range=rows, pair_range=pairs)
     return allreduce_sigma(part)
+
+
+def sharded_apply_host(sector, op, host_coeff: torch.Tensor, host_sigma: torch.Tensor,
+                       mode: str = "det") -> None:
+    """End-to-end sigma with HOST buffers on every rank.
+
+    Each rank uploads only its 1/world row slice of ``host_coeff`` (pinned), the slices
+    are exchanged over NVLink (one broadcast per owner) so that every GPU holds the full
+    coefficient matrix, the sharded sigma build and its all-reduce run on the devices,
+    and each rank downloads its row slice of the result into ``host_sigma``.  Host <->
+    device traffic per rank is 2 * 16 * L^2 / world bytes instead of 2 * 16 * L^2."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        sector.coeff.copy_(host_coeff, non_blocking=True)
+        sigma = sector.apply_operator(op)
+        host_sigma.copy_(sigma, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return
+    rank = dist.get_rank()
+    slices = split_even(sector.lena(), world)
+    r0, r1 = slices[rank]
+    sector.coeff[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
+    for src, (s0, s1) in enumerate(slices):
+        if s1 > s0:
+            dist.broadcast(torch.view_as_real(sector.coeff[s0:s1]), src=src)
+    sigma = sharded_apply(sector, op, mode)
+    host_sigma[r0:r1].copy_(sigma[r0:r1], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
