@@ -129,6 +129,13 @@ class DenseOperator:
                 raise ValueError(f"h2e has shape {h2e.shape}, expected {(norb,) * 4}")
             h2p = numpy.ascontiguousarray(-numpy.moveaxis(h2e.astype(_C128), 1, 2))
             h1p -= numpy.einsum("ikkj->ij", h2p)
+            tol = float(settings.symmetry_tolerance)
+            if tol > 0.0:
+                avg = 0.25 * (h2p + h2p.transpose(1, 0, 2, 3) + h2p.transpose(0, 1, 3, 2) +
+                              h2p.transpose(1, 0, 3, 2))
+                scale = float(numpy.abs(h2p).max())
+                if 0.0 < float(numpy.abs(avg - h2p).max()) <= tol * scale:
+                    h2p = numpy.ascontiguousarray(avg)
             self._h2p = h2p
             h2p_ptr = h2p.ctypes.data
         h1p = numpy.ascontiguousarray(h1p)

@@ -26,3 +26,11 @@ workspace when the whole D tensor does not fit."""
 
 max_workspace_bytes = None
 """Optional hard cap (bytes) on the sigma workspace; None = no cap."""
+
+symmetry_tolerance = 0.0
+"""The contraction runs in the compressed i>=j pair space when the folded two-body tensor
+satisfies h2'[ij,kl] == h2'[ji,kl] == h2'[ij,lk] EXACTLY (real-orbital integrals built by a
+symmetric procedure).  Integrals that are symmetric only up to rounding can opt in by setting
+this to a relative tolerance (e.g. 1e-13): tensors whose asymmetry is below
+tolerance * max|h2'| are symmetrised (averaged) on the host first, which perturbs the
+operator by at most that amount."""

@@ -17,6 +17,10 @@ Outputs (all small, committed):
     ref_unittest_fqe_data.npz   reference's shipped goldens, verbatim values
     ref_graphs.npz              strings / maps / dexc from reference FciGraph
     ref_api.npz                 Wavefunction-level inputs + outputs
+    ref_hring12.npz             BASELINE config 0 (profiling/profile_H_ring.py): integrals read
+                                from profiling/Hring_12.hdf5 with tests/golden/hdf5_mini.py,
+                                energies, and signatures (norms, 512 sampled coefficients, 8
+                                random projections) of H|HF> and of the state evolved to t=0.1
 """
 import os
 import shutil
@@ -219,7 +223,41 @@ def main():
         dch4 = fqe.get_diagonalcoulomb_hamiltonian(h4)
         api[f"{tag}_dc4_apply"] = wfn.apply(dch4).get_coeff((n, sz))
     np.savez_compressed(os.path.join(HERE, "ref_api.npz"), **api)
-    for f in ("ref_unittest_fqe_data.npz", "ref_graphs.npz", "ref_api.npz"):
+
+    # ---- (4) BASELINE.json config 0: H12 ring as run by profiling/profile_H_ring.py ---------
+    sys.path.insert(0, HERE)
+    from hdf5_mini import MiniHDF5
+    mol = MiniHDF5(os.path.join(REF, "profiling", "Hring_12.hdf5"))
+    nele, norbs = int(mol.read("n_electrons")), int(mol.read("n_orbitals"))
+    sz = int(mol.read("multiplicity")) - 1
+    h1 = np.array(mol.read("one_body_integrals"))
+    h2 = np.array(mol.read("two_body_integrals"))
+    e_nuc = float(mol.read("nuclear_repulsion"))
+    h2f = np.ascontiguousarray(np.einsum("ijlk", -0.5 * h2))
+    wf = fqe.Wavefunction([[nele, sz, norbs]])
+    wf.set_wfn(strategy="hartree-fock")
+    wf.normalize()
+    ham = fqe.get_restricted_hamiltonian((h1, h2f), e_0=e_nuc)
+    e_init = wf.expectationValue(ham)
+    sigma = wf.apply(ham).get_coeff((nele, sz))
+    t_evolve = 0.1
+    evolved = wf.time_evolve(t_evolve, ham)
+    e_final = evolved.expectationValue(ham)
+    cev = evolved.get_coeff((nele, sz))
+    rng = np.random.default_rng(20261200)
+    probe = rng.standard_normal((8,) + cev.shape) + 1j * rng.standard_normal((8,) + cev.shape)
+    idx = rng.choice(cev.size, size=512, replace=False)
+    np.savez_compressed(
+        os.path.join(HERE, "ref_hring12.npz"), meta=np.array([nele, sz, norbs]), h1=h1, h2=h2f,
+        e_0=np.array([e_nuc]), hf_energy=np.array([float(mol.read("hf_energy"))]),
+        e_init=np.array([e_init]), e_final=np.array([e_final]), t=np.array([t_evolve]),
+        probe_seed=np.array([20261200]), sample_idx=idx,
+        sigma_samples=sigma.reshape(-1)[idx], sigma_norm=np.array([np.linalg.norm(sigma)]),
+        sigma_probe=np.einsum("kab,ab->k", probe.conj(), sigma),
+        evolved_samples=cev.reshape(-1)[idx], evolved_norm=np.array([np.linalg.norm(cev)]),
+        evolved_probe=np.einsum("kab,ab->k", probe.conj(), cev))
+    print("H12 ring: E_init", e_init, "E_final", e_final, "E_HF(file)", float(mol.read("hf_energy")))
+    for f in ("ref_unittest_fqe_data.npz", "ref_graphs.npz", "ref_api.npz", "ref_hring12.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
