@@ -57,7 +57,24 @@ ms = timed(lambda: sec.norm())
 out["znorm_norb16"] = {"ms": ms, "GBps": 16.0 * la * lb / ms / 1e6}
 ms = timed(lambda: sec.axpy_norm(1e-6, other))
 out["axpy_norm_norb16"] = {"ms": ms, "GBps": 48.0 * la * lb / ms / 1e6}
-del wfn, sec, other
+
+# ---- config 3: one Trotter step of a double-factorised H = orbital rotation o DC evolve ------
+rng = np.random.default_rng(3)
+kmat = rng.standard_normal((norb, norb))
+kmat = 0.5 * (kmat + kmat.T)
+rot_ham = fqe.get_restricted_hamiltonian((kmat,))
+dc_ham = fqe.get_diagonalcoulomb_hamiltonian(vij)
+ms = timed(lambda: sec.apply((kmat,)), reps=3, warm=1)
+out["one_body_sigma_norb16"] = {"ms": ms}
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+step = wfn.time_evolve(0.01, rot_ham)
+step = step.time_evolve(0.01, dc_ham, inplace=True)
+torch.cuda.synchronize()
+out["trotter_step_norb16"] = {"seconds": time.perf_counter() - t0,
+                              "rotation_taylor_terms": wfn.last_expansion_order,
+                              "norm_after": step.norm()}
+del wfn, sec, other, step
 torch.cuda.empty_cache()
 
 # ---- config 2: norb=14 sigma + Taylor time_evolve -----------------------------------------
