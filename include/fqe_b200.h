@@ -107,6 +107,12 @@ int fqeb_graph_device_tables(const fqeb_graph *g, int spin,
  * ------------------------------------------------------------------------ */
 int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p,
                    fqeb_op **out);
+/* Same with flags: FQEB_OP_FLAG_FULL_PAIR_SPACE keeps the norb^2 pair space even when the
+ * tensor is pair-symmetric (for callers that hand-build D / E in the reference layout, e.g.
+ * the 3-body apply, fqe_data.py:1199-1208). */
+enum { FQEB_OP_FLAG_FULL_PAIR_SPACE = 1 };
+int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_h2p, int flags,
+                      fqeb_op **out);
 int fqeb_op_destroy(fqeb_op *op);
 int fqeb_op_kind(const fqeb_op *op, int *kind);
 /* Size of the pair space the contraction runs over and whether it is compressed:

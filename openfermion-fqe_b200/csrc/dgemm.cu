@@ -1006,6 +1006,11 @@ extern "C" int fqeb_contract_dvec_rows(const fqeb_op *op, int nij) {
 }
 
 extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p, fqeb_op **out) {
+  return fqeb_op_create_ex(norb, h_h1p, h_h2p, 0, out);
+}
+
+extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_h2p, int flags,
+                                 fqeb_op **out) {
   FQEB_REQUIRE(out != nullptr, "fqeb_op_create: out is NULL");
   *out = nullptr;
   FQEB_REQUIRE(norb >= 1 && norb <= kMaxOrb, "fqeb_op_create: norb=%d outside [1,%d]", norb,
@@ -1057,7 +1062,7 @@ extern "C" int fqeb_op_create(int norb, const double *h_h1p, const double *h_h2p
     // integrals.  Then E[ij] == E[ji] and only i>=j pairs are contracted, against
     // D[ij]+D[ji]: the compressed algorithm of the reference's real branch
     // (fqe_data.py:659-681), valid here for any coefficient class.
-    bool sym = getenv("FQEB_NO_SYMMETRY") == nullptr;
+    bool sym = getenv("FQEB_NO_SYMMETRY") == nullptr && !(flags & FQEB_OP_FLAG_FULL_PAIR_SPACE);
     for (int i = 0; i < norb && sym; ++i)
       for (int j = 0; j < norb && sym; ++j)
         for (int k = 0; k < norb && sym; ++k)

@@ -300,6 +300,89 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
   out[x * lenb + b] = s;
 }
 
+// One-body operator, sigma[a,b] = sum_ij h1[ij] * D[ij,a,b], without ever forming D:
+// the compact per-string excitation lists give exactly lk_a coalesced row reads and lk_b
+// in-row gathers per element (instead of probing all norb^2 pairs).  This is
+// FqeData._apply_array_spatial1 (fqe_data.py:477-530) and the inner step of the Taylor
+// series for quadratic Hamiltonians / orbital rotations.
+__global__ void __launch_bounds__(kTB, 3)
+k_apply_one_body(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
+                 const int2 *__restrict__ clistT_a, const int2 *__restrict__ clist_b,
+                 const double2 *__restrict__ h1, const double2 *__restrict__ coeff, int64_t row0,
+                 int nbt, double2 *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_raw1[];
+  double2 *s_h1 = reinterpret_cast<double2 *>(s_raw1);            // [npair]
+  int2 *s_alpha = reinterpret_cast<int2 *>(s_h1 + npair);         // [lk_a]
+  const int64_t tile = blockIdx.x;
+  const int64_t a = row0 + tile / nbt;
+  for (int p = threadIdx.x; p < npair; p += kTB) s_h1[p] = h1[p];
+  for (int sl = threadIdx.x; sl < lk_a; sl += kTB) s_alpha[sl] = clistT_a[a * (int64_t)lk_a + sl];
+  __syncthreads();
+  const int64_t b = (tile % nbt) * kTB + threadIdx.x;
+  if (b >= lenb) return;
+  const double2 *__restrict__ ccol = coeff + b;
+  const double2 *__restrict__ crow = coeff + a * lenb;
+  double2 acc = make_double2(0.0, 0.0);
+  constexpr int U = 8;
+  auto fma_c = [&](double2 h, int sy, double2 v) {
+    const double sg = sy < 0 ? -1.0 : 1.0;
+    acc.x += sg * (h.x * v.x - h.y * v.y);
+    acc.y += sg * (h.x * v.y + h.y * v.x);
+  };
+  int sl = 0;
+  for (; sl + U <= lk_a; sl += U) {
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      v[u] = ldg_c128(ccol + (int64_t)(abs(s_alpha[sl + u].y) - 1) * lenb);
+#pragma unroll
+    for (int u = 0; u < U; ++u) fma_c(s_h1[s_alpha[sl + u].x], s_alpha[sl + u].y, v[u]);
+  }
+  for (; sl < lk_a; ++sl)
+    fma_c(s_h1[s_alpha[sl].x], s_alpha[sl].y, ccol[(int64_t)(abs(s_alpha[sl].y) - 1) * lenb]);
+  const int2 *__restrict__ cl = clist_b + b;
+  sl = 0;
+  for (; sl + U <= lk_b; sl += U) {
+    int2 e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = ldg_int2(cl + (int64_t)(sl + u) * lenb);
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ldg_c128(crow + (abs(e[u].y) - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u) fma_c(s_h1[e[u].x], e[u].y, v[u]);
+  }
+  for (; sl < lk_b; ++sl) {
+    const int2 e = cl[(int64_t)sl * lenb];
+    fma_c(s_h1[e.x], e.y, crow[abs(e.y) - 1]);
+  }
+  double2 sv = out[a * lenb + b];
+  sv.x += acc.x;
+  sv.y += acc.y;
+  out[a * lenb + b] = sv;
+}
+
+// sigma rows [row0, row0+nrows) += h1 applied to C (all pairs)
+int launch_one_body(const fqeb_graph *g, const double *d_coeff, const double *d_h1, int64_t row0,
+                    int64_t nrows, double *d_out, cudaStream_t st) {
+  const int npair = g->norb * g->norb;
+  const int64_t lena = g->len[0], lenb = g->len[1];
+  FQEB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= lena, "one_body: bad row range");
+  if (nrows == 0 || npair == 0) return FQEB_OK;
+  const int nbt = (int)((lenb + kTB - 1) / kTB);
+  const int64_t tiles = nrows * nbt;
+  FQEB_REQUIRE(tiles < (1ll << 31), "one_body: problem too large for one launch");
+  const size_t smem = sizeof(double2) * (size_t)npair + sizeof(int2) * (size_t)g->lk[0];
+  if (smem > 48 * 1024)
+    FQEB_CUDA(cudaFuncSetAttribute(k_apply_one_body, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  k_apply_one_body<<<(unsigned)tiles, kTB, smem, st>>>(
+      npair, lena, lenb, g->lk[0], g->lk[1], g->d_clistT[0], g->d_clist[1],
+      (const double2 *)d_h1, (const double2 *)d_coeff, row0, nbt, (double2 *)d_out);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
 // pairs == nullptr: identity pair list of the graph (D row c <-> pair c), np_eff = norb^2
 int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
                      int64_t row0, int64_t nrows, int ij0, int ij1, const int32_t *d_pairs,

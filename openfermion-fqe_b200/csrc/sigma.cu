@@ -29,6 +29,8 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
 int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t pitch,
                       int64_t row0, int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
                       double *d_out, cudaStream_t st);
+int launch_one_body(const fqeb_graph *g, const double *d_coeff, const double *d_h1, int64_t row0,
+                    int64_t nrows, double *d_out, cudaStream_t st);
 int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
                  int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde, int ij0,
                  int ij1, cudaStream_t st);
@@ -159,7 +161,11 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   if (row0 == row1 || ij0 == ij1) return FQEB_OK;
 
   if (!op->has_h2) {
-    // one-body operator: sigma = sum_ij h1[ij] D[ij], D never materialised
+    // one-body operator: sigma = sum_ij h1[ij] D[ij], D never materialised.  The whole pair
+    // range goes through the compact-list kernel; a pair slice (ij-sharded run) through the
+    // gather kernel with stores disabled.
+    if (ij0 == 0 && ij1 == op->np)
+      return launch_one_body(g, d_coeff, op->d_h1, row0, row1 - row0, d_sigma, st);
     return launch_make_dvec(g, d_coeff, nullptr, 0, row0, row1 - row0, ij0, ij1, op->d_pairs,
                             op->np, op->d_h1, d_sigma, st);
   }

@@ -152,6 +152,32 @@ class DenseOperator:
         self.npair = int(npairs.value)      # pair space of the contraction
         self.symmetric = bool(sym.value)    # i>=j compressed (real-orbital integrals)
 
+    @classmethod
+    def from_folded(cls, norb: int, h1p: numpy.ndarray, h2p: Optional[numpy.ndarray],
+                    full_pair_space: bool = False):
+        """Operator from ALREADY folded tensors: E[ij] = sum_kl h2p[i,j,k,l] D[k,l] and
+        sigma += sum_ij h1p[i,j] D[i,j] (no moveaxis / trace folding applied).
+        ``full_pair_space`` keeps the norb^2 pair space even for pair-symmetric tensors."""
+        self = cls.__new__(cls)
+        _require_cuda()
+        h1p = numpy.ascontiguousarray(numpy.asarray(h1p), dtype=_C128)
+        self._h2p = None
+        ptr = None
+        if h2p is not None:
+            self._h2p = numpy.ascontiguousarray(numpy.asarray(h2p), dtype=_C128)
+            ptr = self._h2p.ctypes.data
+        self.norb = norb
+        self.has_h2 = h2p is not None
+        handle = ctypes.c_void_p()
+        _lib.call("fqeb_op_create_ex", norb, h1p.ctypes.data, ptr,
+                  _lib.OP_FLAG_FULL_PAIR_SPACE if full_pair_space else 0, ctypes.byref(handle))
+        self._handle = handle
+        kind, npairs, sym = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.call("fqeb_op_kind", handle, ctypes.byref(kind))
+        _lib.call("fqeb_op_pair_space", handle, ctypes.byref(npairs), ctypes.byref(sym))
+        self.kind, self.npair, self.symmetric = int(kind.value), int(npairs.value), bool(sym.value)
+        return self
+
     @property
     def handle(self) -> ctypes.c_void_p:
         return self._handle
@@ -164,6 +190,12 @@ class DenseOperator:
             except Exception:
                 pass
             self._handle = None
+
+
+def op_factor(op: DenseOperator) -> complex:
+    """Scalar the contraction factors out of the operator: i for purely imaginary
+    tensors (their imaginary part is contracted as a real matrix), else 1."""
+    return 1.0j if op.kind == _lib.OP_IMAG else 1.0 + 0.0j
 
 
 class FqeData:
@@ -366,8 +398,10 @@ class FqeData:
             self.coeff = self._apply_array_spatial1(array[0])
         elif len_arr == 2:
             self.coeff = self._apply_array_spatial12(array[0], array[1])
+        elif len_arr == 3:
+            self.coeff = self._apply_array_spatial123(array[0], array[1], array[2])
         else:
-            raise NotImplementedError("3- and 4-body dense operators are outside the B200 hot path")
+            raise NotImplementedError("4-body dense operators are outside the B200 hot path")
 
     def apply_operator(self, op: DenseOperator, row_range=None, pair_range=None) -> torch.Tensor:
         """sigma for a prepared operator.  ``row_range`` / ``pair_range`` restrict the
@@ -400,6 +434,59 @@ class FqeData:
         assert h1e.shape == (norb, norb)
         assert h2e.shape == (norb, norb, norb, norb)
         return self.apply_operator(DenseOperator(norb, h1e, h2e))
+
+    def _apply_array_spatial123(self, h1e: numpy.ndarray, h2e: numpy.ndarray,
+                                h3e: numpy.ndarray) -> torch.Tensor:
+        """1- through 3-body dense spatial operator (fqe_data.py:1166-1216; the shape of
+        reference profiling/profile_3_body.py).  The three-body part is
+            - scatter( sum_ij  h3[:, q, i, :, s, j] . gather( gather(C)[i, j] ) )
+        i.e. norb^2 gather -> DMMA contraction passes accumulated into one E tensor and one
+        scatter, all with the kernels of the 1+2-body path; the lower-rank pieces of
+        normal ordering are folded into (h1, h2) on the host first."""
+        dev = _require_cuda()
+        norb = self.norb()
+        h3e = numpy.asarray(h3e)
+        if h3e.shape != (norb,) * 6:
+            raise ValueError(f"h3e has shape {h3e.shape}, expected {(norb,) * 6}")
+        nh1 = numpy.array(h1e, dtype=_C128)
+        nh2 = numpy.array(h2e, dtype=_C128)
+        # fqe_data.py:1184-1191, vectorised over the loop indices
+        nh2 += -numpy.einsum("kjiiab->jkab", h3e) - numpy.einsum("jikiab->jkab", h3e) \
+            - numpy.einsum("jkiaib->jkab", h3e)
+        nh1 += numpy.einsum("aijijb->ab", h3e)
+        out = self._apply_array_spatial12(nh1, nh2)
+
+        lib = _lib.load()
+        npair = norb * norb
+        ndet = self.lena() * self.lenb()
+        align = int(lib.fqeb_gemm_col_align())
+        ld = (ndet + align - 1) // align * align
+        dvec0 = self.calculate_dvec_spatial()                       # [norb, norb, lena, lenb]
+        zero_h1 = numpy.zeros((norb, norb), dtype=_C128)
+        acc = torch.zeros((npair + 8, ld), dtype=torch.complex128, device=dev)
+        evec = torch.empty_like(acc)
+        dvec2 = None
+        for i in range(norb):
+            for j in range(norb):
+                m = numpy.ascontiguousarray(h3e[:, :, i, :, :, j].transpose(0, 2, 1, 3),
+                                            dtype=_C128)            # [(p, r), (q, s)]
+                if not m.any():
+                    continue
+                op = DenseOperator.from_folded(norb, zero_h1, m, full_pair_space=True)
+                rows = int(lib.fqeb_contract_dvec_rows(op.handle, npair))
+                if dvec2 is None or dvec2.shape[0] < rows:
+                    dvec2 = torch.zeros((rows, ld), dtype=torch.complex128, device=dev)
+                _lib.call("fqeb_make_dvec", self._core.handle,
+                          self._check_coeff(dvec0[i, j]).data_ptr(), dvec2.data_ptr(), ld, 0,
+                          self.lena(), 0, npair, _stream())
+                _lib.call("fqeb_contract", op.handle, dvec2.data_ptr(), ld, evec.data_ptr(), ld,
+                          ndet, 0, npair, _stream())
+                factor = op_factor(op)
+                _lib.call("fqeb_zaxpy", acc.numel(), factor.real, factor.imag, evec.data_ptr(),
+                          acc.data_ptr(), _stream())
+        _lib.call("fqeb_make_coeff", self._core.handle, acc.data_ptr(), ld, 0, self.lena(), -1.0,
+                  0.0, out.data_ptr(), _stream())
+        return out
 
     # ---- dvec / coeff (fqe_data.py:2149-2160, 2209-2234, 2309-2334) -----------------
     def calculate_dvec_spatial(self) -> torch.Tensor:

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libfqe_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_CONVERGE = range(6)
 OP_REAL, OP_IMAG, OP_COMPLEX = 0, 1, 2
+OP_FLAG_FULL_PAIR_SPACE = 1
 
 
 class FqeB200Error(RuntimeError):
@@ -43,6 +44,7 @@ SIGNATURES = {
     "fqeb_graph_device_tables": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p),
                                          POINTER(c_void_p)]),
     "fqeb_op_create": (c_int, [c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "fqeb_op_create_ex": (c_int, [c_int, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "fqeb_op_destroy": (c_int, [c_void_p]),
     "fqeb_op_kind": (c_int, [c_void_p, POINTER(c_int)]),
     "fqeb_op_pair_space": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),

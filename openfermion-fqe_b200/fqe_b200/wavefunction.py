@@ -212,7 +212,8 @@ class Wavefunction:
         if len(array) < 1 or len(array) > 4:
             raise ValueError("Number of operators in tuple must be between 1 and 4.")
         if len(array) > 2:
-            raise NotImplementedError("3- and 4-body dense operators are outside the B200 hot path")
+            raise NotImplementedError("prepared operators cover 1- and 2-body tensors; "
+                                      "3-body tuples go through FqeData.apply")
         if array[0].shape[0] != self._norb:
             raise NotImplementedError("only spatial-orbital (restricted) tensors are supported")
         return DenseOperator(self._norb, array[0], array[1] if len(array) == 2 else None)
@@ -226,6 +227,15 @@ class Wavefunction:
         return out
 
     def _apply_array(self, array: Tuple[numpy.ndarray, ...], e_0: complex) -> 'Wavefunction':
+        if len(array) == 3:
+            if array[0].shape[0] != self._norb:
+                raise NotImplementedError("only spatial-orbital (restricted) tensors are supported")
+            out = self.empty_copy(zero=False)
+            for key, sec in self._civec.items():
+                out._civec[key].coeff = sec._apply_array_spatial123(array[0], array[1], array[2])
+            if numpy.abs(e_0) > 1.e-15:
+                out.ax_plus_y(e_0, self)
+            return out
         return self._apply_operator(self._dense_operator(array), e_0)
 
     def _apply_diagonal_coulomb(self, hamil: diagonal_coulomb.DiagonalCoulomb) -> 'Wavefunction':
@@ -260,11 +270,13 @@ class Wavefunction:
             # -i*t*H is purely imaginary for real integrals: the operator is prepared
             # once (real-GEMM mode) and reused by every term.  The tuple re-wrap of the
             # reference drops e_0 inside the loop (fqe_decorators.py:68-73).
-            op = self._dense_operator(hamil.iht(time))
+            ham_arrays = hamil.iht(time)
+            op = self._dense_operator(ham_arrays) if len(ham_arrays) <= 2 else None
             time_evol = copy.deepcopy(base)
             work = copy.deepcopy(base)
             for order in range(1, expansion):
-                work = work._apply_operator(op)
+                work = work._apply_operator(op) if op is not None else \
+                    work._apply_array(ham_arrays, 0.0)
                 coeff = 1.0 / factorial(order)
                 wnorm = time_evol._axpy_norm(coeff, work)
                 if wnorm * numpy.abs(coeff) < accuracy:
@@ -278,19 +290,23 @@ class Wavefunction:
             wprime = 0.9875
             ascale = (spec_lim[1] - spec_lim[0]) / (2.0 * wprime)
             eshift = -(spec_lim[0] + ascale * wprime)
-            op = self._dense_operator(hamil.tensors())
+            tensors = hamil.tensors()
             e_0 = hamil.e_0()
+            op = self._dense_operator(tensors) if len(tensors) <= 2 else None
+
+            def _h(x: 'Wavefunction') -> 'Wavefunction':
+                return x._apply_operator(op, e_0) if op is not None else x._apply_array(tensors, e_0)
 
             time_evol = copy.deepcopy(base)
             time_evol.scale(jv(0, ascale * time))
             minus = copy.deepcopy(base)
-            current = minus._apply_operator(op, e_0)
+            current = _h(minus)
             current.ax_plus_y(eshift, minus)
             current.scale(1.0 / ascale)
             time_evol.ax_plus_y(2.0 * jv(1, ascale * time) * (-1.j), current)
             for order in range(2, expansion):
                 minus.scale(-1.0)
-                minus.ax_plus_y(2.0 / ascale, current._apply_operator(op, e_0))
+                minus.ax_plus_y(2.0 / ascale, _h(current))
                 minus.ax_plus_y(2.0 * eshift / ascale, current)
                 current, minus = minus, current
                 coeff = 2.0 * jv(order, ascale * time) * (-1.j)**order

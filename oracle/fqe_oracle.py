@@ -243,6 +243,39 @@ def sigma_restricted(g: OracleGraph, coeff: np.ndarray, h1: np.ndarray,
     return out
 
 
+def fold_three_body(h1: np.ndarray, h2: np.ndarray, h3: np.ndarray):
+    """Lower-rank pieces that normal-ordering the three-body term feeds into h1 and h2
+    (fqe_data.py:1180-1191; the reference re-evaluates the 1+2-body apply inside its i loop,
+    only the fully accumulated tensors of the last pass matter)."""
+    n = h1.shape[0]
+    nh1 = np.array(h1, dtype=np.complex128)
+    nh2 = np.array(h2, dtype=np.complex128)
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                nh2[j, k, :, :] += (-h3[k, j, i, i, :, :] - h3[j, i, k, i, :, :] -
+                                    h3[j, k, i, :, i, :])
+            nh1[:, :] += h3[:, i, j, i, j, :]
+    return nh1, nh2
+
+
+def sigma_restricted_123(g: OracleGraph, coeff: np.ndarray, h1: np.ndarray, h2: np.ndarray,
+                         h3: np.ndarray) -> np.ndarray:
+    """FqeData.apply((h1,h2,h3)) = _apply_array_spatial123 (fqe_data.py:1166-1216):
+    out = apply12(nh1, nh2) - scatter( sum_ij h3[:,q,i,:,s,j] . gather(gather(C)[i,j]) )."""
+    n = g.norb
+    coeff = np.asarray(coeff, dtype=np.complex128)
+    nh1, nh2 = fold_three_body(h1, h2, np.asarray(h3, dtype=np.complex128))
+    out = sigma_restricted(g, coeff, nh1, nh2)
+    odvec = dvec_spatial(g, coeff)
+    acc = np.zeros_like(odvec)
+    for i in range(n):
+        for j in range(n):
+            tmp2 = dvec_spatial(g, odvec[i, j])
+            acc += np.tensordot(h3[:, :, i, :, :, j], tmp2, axes=((1, 3), (0, 1)))
+    return out - coeff_from_dvec(g, acc)
+
+
 def sigma_one_body(g: OracleGraph, coeff: np.ndarray,
                    h1: np.ndarray) -> np.ndarray:
     """FqeData.apply((h1,)) (fqe_data.py:477-530)."""

@@ -222,6 +222,26 @@ def main():
                 h4[i, j, i, j] = -vij[i, j]
         dch4 = fqe.get_diagonalcoulomb_hamiltonian(h4)
         api[f"{tag}_dc4_apply"] = wfn.apply(dch4).get_coeff((n, sz))
+    # ---- dense three-body apply (BASELINE config 5 shape: profiling/profile_3_body.py) ------
+    for tag, n, sz, norb in [("t3a", 4, 0, 4), ("t3b", 5, 1, 5), ("t3c", 6, 0, 6)]:
+        rng = np.random.default_rng(20260500 + norb)
+        h1 = rng.standard_normal((norb,) * 2) + 1j * rng.standard_normal((norb,) * 2)
+        h2 = 0.1 * (rng.standard_normal((norb,) * 4) + 1j * rng.standard_normal((norb,) * 4))
+        if tag == "t3c":   # the profiling script's tensor, h1 = h2 = 0
+            idx = np.indices((norb,) * 6)
+            h3 = ((idx[0] + idx[3]) * (idx[1] + idx[4]) * (idx[2] + idx[5]) * 0.002).astype(
+                np.complex128)
+            h1 = np.zeros_like(h1)
+            h2 = np.zeros_like(h2)
+        else:
+            h3 = 0.05 * (rng.standard_normal((norb,) * 6) + 1j * rng.standard_normal((norb,) * 6))
+        wfn = fqe.Wavefunction([[n, sz, norb]])
+        shape = wfn.get_coeff((n, sz)).shape
+        c0 = rand_state(shape, rng)
+        wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0.copy()})
+        api[f"{tag}_meta"] = np.array([n, sz, norb], dtype=np.int64)
+        api[f"{tag}_h1"], api[f"{tag}_h2"], api[f"{tag}_h3"], api[f"{tag}_c0"] = h1, h2, h3, c0
+        api[f"{tag}_sigma"] = wfn.apply((h1, h2, h3)).get_coeff((n, sz))
     np.savez_compressed(os.path.join(HERE, "ref_api.npz"), **api)
 
     # ---- (4) BASELINE.json config 0: H12 ring as run by profiling/profile_H_ring.py ---------

@@ -78,3 +78,61 @@ def test_config3_trotter_step_small():
     ref = O.time_evolve_dc(g, ref, dt, np.zeros(norb), vij)
     assert O.rel_err(out, ref) < 1e-10
     assert abs(np.linalg.norm(out) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["t3a", "t3b", "t3c"])
+def test_config5_dense_three_body_matches_reference_api(golden_dir, tag):
+    """wfn.apply((h1, h2, h3)) against outputs of the reference's own API; t3c is the tensor
+    of profiling/profile_3_body.py (h1 = h2 = 0)"""
+    import fqe_b200 as fqe
+    api = np.load(os.path.join(golden_dir, "ref_api.npz"))
+    n, sz, norb = [int(x) for x in api[f"{tag}_meta"]]
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): api[f"{tag}_c0"]})
+    out = wfn.apply((api[f"{tag}_h1"], api[f"{tag}_h2"], api[f"{tag}_h3"])).get_coeff((n, sz))
+    assert O.rel_err(out, api[f"{tag}_sigma"]) < 1e-11
+    out = wfn.sector((n, sz)).apply((api[f"{tag}_h1"], api[f"{tag}_h2"], api[f"{tag}_h3"]))
+    assert O.rel_err(out.to_numpy(), api[f"{tag}_sigma"]) < 1e-11
+
+
+def test_config5_three_body_vs_oracle_norb7():
+    import fqe_b200 as fqe
+    from fqe_b200 import synth
+    norb, n, sz = 7, 7, 1
+    g = O.graph(4, 3, norb)
+    rng = np.random.default_rng(55)
+    h1 = rng.standard_normal((norb,) * 2)
+    h2 = 0.1 * rng.standard_normal((norb,) * 4)
+    h3 = 0.02 * (rng.standard_normal((norb,) * 6) + 1j * rng.standard_normal((norb,) * 6))
+    c = synth.state(g.lena, g.lenb, seed=9)
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c})
+    out = wfn.apply((h1, h2, h3)).get_coeff((n, sz))
+    assert O.rel_err(out, O.sigma_restricted_123(g, c, h1, h2, h3)) < 1e-11
+
+
+def test_three_body_time_evolve_small():
+    """Taylor evolution under a Hermitian 1+2+3-body operator against the exact exponential"""
+    import fqe_b200 as fqe
+    from fqe_b200 import synth
+    norb, n, sz = 4, 4, 0
+    g = O.graph(2, 2, norb)
+    rng = np.random.default_rng(77)
+    h1, h2 = synth.integrals(norb, "herm")
+    w = rng.standard_normal((norb,) * 6) + 1j * rng.standard_normal((norb,) * 6)
+    h3 = 0.02 * (w + w.conj().transpose(5, 4, 3, 2, 1, 0))   # a+a+a+ a a a hermitian
+    c = synth.state(g.lena, g.lenb, seed=2)
+    dim = c.size
+    hm = np.zeros((dim, dim), dtype=np.complex128)
+    for col in range(dim):
+        e = np.zeros(dim, dtype=np.complex128)
+        e[col] = 1.0
+        hm[:, col] = O.sigma_restricted_123(g, e.reshape(c.shape), h1, h2, h3).reshape(-1)
+    assert np.allclose(hm, hm.conj().T, atol=1e-12)
+    wv, vv = np.linalg.eigh(hm)
+    t = 0.05
+    ref = ((vv * np.exp(-1j * t * wv)) @ (vv.conj().T @ c.reshape(-1))).reshape(c.shape)
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c})
+    out = wfn.time_evolve(t, fqe.get_restricted_hamiltonian((h1, h2, h3)))
+    assert O.rel_err(out.get_coeff((n, sz)), ref) < 1e-10

@@ -278,3 +278,26 @@ def test_fusion_requires_absorbable_one_body_term():
     assert O.rel_err(out, O.sigma_restricted(g, c, h1n, h2)) < TOL
     out = d.apply((h1n.real.copy(), h2)).to_numpy()     # real but non-symmetric h1
     assert O.rel_err(out, O.sigma_restricted(g, c, h1n.real, h2)) < TOL
+
+
+def test_one_body_shards():
+    """one-body operator: full range (compact-list kernel) equals the sum of row shards and of
+    pair slices (gather kernel with stores disabled)"""
+    from fqe_b200 import lib as L
+    from fqe_b200 import synth
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    na, nb, norb = 4, 3, 7
+    h1, _ = synth.integrals(norb, "herm")
+    g = O.graph(na, nb, norb)
+    c = synth.state(g.lena, g.lenb, seed=21)
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    op = DenseOperator(norb, h1, None)
+    ref = O.sigma_one_body(g, c, h1)
+    full = d.apply_operator(op)
+    assert O.rel_err(full.cpu().numpy(), ref) < TOL
+    la, npair = d.lena(), op.npair
+    rows = d.apply_operator(op, row_range=(0, 11)) + d.apply_operator(op, row_range=(11, la))
+    assert O.rel_err(rows.cpu().numpy(), ref) < TOL
+    pairs = d.apply_operator(op, pair_range=(0, 20)) + d.apply_operator(op, pair_range=(20, npair))
+    assert O.rel_err(pairs.cpu().numpy(), ref) < TOL

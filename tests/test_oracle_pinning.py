@@ -173,3 +173,13 @@ def test_numpy_vs_ref_c_random(cfg):
     v = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
     assert O.rel_err(O.dc_apply(g, c, diag, v), R.dc_apply(rg, c, diag, v)) < TOL
     assert O.rel_err(O.dc_evolve(g, c, 0.1 * diag, 0.1 * v), R.dc_evolve(rg, c, 0.1 * diag, 0.1 * v)) < TOL
+
+
+@pytest.mark.parametrize("tag", ["t3a", "t3b", "t3c"])
+def test_three_body_api_goldens(api, tag):
+    """dense 3-body apply restatement vs outputs of the reference's wfn.apply((h1,h2,h3))"""
+    n, sz, norb = [int(x) for x in api[f"{tag}_meta"]]
+    g = O.graph((n + sz) // 2, (n - sz) // 2, norb)
+    out = O.sigma_restricted_123(g, api[f"{tag}_c0"], api[f"{tag}_h1"], api[f"{tag}_h2"],
+                                 api[f"{tag}_h3"])
+    assert O.rel_err(out, api[f"{tag}_sigma"]) < 1e-12
