@@ -174,7 +174,7 @@ def run_reference(args):
         "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * mean_s, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.norb, args.kind), "norb": args.norb,
                    "kind": args.kind},
         "cpu_baseline": {"value": value, "unit": "sigma/s", "cores": cores, "kind": "reference",
@@ -391,7 +391,7 @@ def run_b200(args):
         "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": main["ms_total"] / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64 DMMA)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
             "workload": workload_name(args.norb, args.kind), "norb": args.norb,
