@@ -553,7 +553,7 @@ struct GemmShape {
 static const GemmShape kShapes[] = {{2, 8}, {1, 18}, {1, 17}, {1, 14}, {1, 13}, {1, 10}};
 
 template <bool CPLX, int WARPS_M, int WM, int WN, int KS, int NST>
-static int launch_ws(const fqeb_op *op, int a_col0, const double *d_dvec, int64_t ldd,
+static int launch_ws(const fqeb_op *op, const double *d_A, int a_col0, const double *d_dvec, int64_t ldd,
                      double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
                      cudaStream_t st) {
   constexpr int BM = WARPS_M * WM * 8;
@@ -576,7 +576,7 @@ static int launch_ws(const fqeb_op *op, int a_col0, const double *d_dvec, int64_
   int64_t grid = sm_count();
   if (grid > nmb) grid -= grid % nmb;
   if (grid > tiles) grid = tiles;
-  kern<<<(unsigned)grid, 320, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+  kern<<<(unsigned)grid, 320, SMEM, st>>>(d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
                                           (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
                                           tiles);
   FQEB_CHECK_LAUNCH();
@@ -584,7 +584,7 @@ static int launch_ws(const fqeb_op *op, int a_col0, const double *d_dvec, int64_
 }
 
 template <bool CPLX, int WARPS_M, int WM, int WN>
-static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int64_t ldd,
+static int launch_shape(const fqeb_op *op, const double *d_A, int a_col0, const double *d_dvec, int64_t ldd,
                         double *d_evec, int64_t lde, int m_valid, int k_valid, int64_t nnb,
                         cudaStream_t st) {
   constexpr int BM = WARPS_M * WM * 8;
@@ -596,12 +596,12 @@ static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int
   static const int pipe = getenv("FQEB_GEMM_PIPE") ? atoi(getenv("FQEB_GEMM_PIPE")) : 1;
   if (ws) {
     if (pipe == 1)
-      return launch_ws<CPLX, WARPS_M, WM, WN, 32, 3>(op, a_col0, d_dvec, ldd, d_evec, lde,
+      return launch_ws<CPLX, WARPS_M, WM, WN, 32, 3>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde,
                                                      m_valid, k_valid, nnb, st);
     if (pipe == 2)
-      return launch_ws<CPLX, WARPS_M, WM, WN, 16, 5>(op, a_col0, d_dvec, ldd, d_evec, lde,
+      return launch_ws<CPLX, WARPS_M, WM, WN, 16, 5>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde,
                                                      m_valid, k_valid, nnb, st);
-    return launch_ws<CPLX, WARPS_M, WM, WN, 16, 4>(op, a_col0, d_dvec, ldd, d_evec, lde, m_valid,
+    return launch_ws<CPLX, WARPS_M, WM, WN, 16, 4>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde, m_valid,
                                                    k_valid, nnb, st);
   }
   constexpr size_t SMEM = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES;
@@ -628,7 +628,7 @@ static int launch_shape(const fqeb_op *op, int a_col0, const double *d_dvec, int
     if (grid > tiles) grid = tiles;
   }
   FQEB_REQUIRE(grid < (1ll << 31), "contract: too many tiles for one launch");
-  kern<<<(unsigned)grid, 256, SMEM, st>>>(op->d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+  kern<<<(unsigned)grid, 256, SMEM, st>>>(d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
                                           (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
                                           tiles);
   FQEB_CHECK_LAUNCH();
@@ -902,7 +902,7 @@ static int launch_fused_wm(const double *d_A, int lda, int a_col0, int c_first, 
 }
 
 // fused gather + contraction of alpha rows [row0, row0+nrows) for pairs [ij0, ij1).
-// d_A: operand with the one-body term absorbed (see fused_operand in sigma.cu).
+// d_A: operand with the one-body term absorbed (absorbed_operand).
 int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
                  int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde, int ij0,
                  int ij1, cudaStream_t st) {
@@ -936,9 +936,12 @@ bool fused_shape_ok(const fqeb_op *op) {
   return sh.warps_m == 1 && m_valid <= sh.bm();
 }
 
-int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
-                    int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st) {
+// d_A: operand override (absorbed_operand), or nullptr for the operator's own h2' operand
+int launch_contract(const fqeb_op *op, const double *d_A, const double *d_dvec, int64_t ldd,
+                    double *d_evec, int64_t lde, int64_t ncols, int ij0, int ij1,
+                    cudaStream_t st) {
   const int np = op->np;
+  if (!d_A) d_A = op->d_A;
   FQEB_REQUIRE(op->has_h2, "contract: operator has no two-body part");
   FQEB_REQUIRE(ij0 >= 0 && ij0 < ij1 && ij1 <= np, "contract: pair slice [%d,%d) invalid", ij0,
                ij1);
@@ -961,14 +964,14 @@ int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double
   FQEB_REQUIRE(padded_rows(sh, m_valid) <= op->Mp, "contract: operator row padding too small");
 #define FQEB_SHAPE_BOTH(WMV, WARPSM, WNV)                                                      \
   if (sh.warps_m == WARPSM && sh.wm == WMV) {                                                  \
-    return cplx ? launch_shape<true, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,   \
+    return cplx ? launch_shape<true, WARPSM, WMV, WNV>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde,   \
                                                        m_valid, k_valid, nnb, st)              \
-                : launch_shape<false, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,  \
+                : launch_shape<false, WARPSM, WMV, WNV>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde,  \
                                                         m_valid, k_valid, nnb, st);            \
   }
 #define FQEB_SHAPE_REAL(WMV, WARPSM, WNV)                                                      \
   if (!cplx && sh.warps_m == WARPSM && sh.wm == WMV) {                                         \
-    return launch_shape<false, WARPSM, WMV, WNV>(op, a_col0, d_dvec, ldd, d_evec, lde,         \
+    return launch_shape<false, WARPSM, WMV, WNV>(op, d_A, a_col0, d_dvec, ldd, d_evec, lde,         \
                                                  m_valid, k_valid, nnb, st);                   \
   }
   FQEB_SHAPE_BOTH(8, 2, 4)
@@ -1154,22 +1157,28 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
       return fail(FQEB_ERR_CUDA);
     }
   }
-  // fused gather+contraction eligibility: single row block, real/imaginary class, and a
-  // one-body term that can be absorbed into the operand without leaving that class
-  // (and, in the compressed pair space, without breaking the i<->j symmetry)
-  op->fuse_ok = false;
-  if (op->has_h2 && fused_shape_ok(op)) {
-    const int part_zero = op->kind == FQEB_OP_IMAG ? 0 : 1;  // component of h1' that must vanish
+  // Can the one-body term be absorbed into the contraction operand,
+  //     A[c, d] += h1'[pair(c)] / n_elec   for every diagonal pair d = (k, k)
+  // (exact on a fixed-particle-number sector because sum_k E_kk = n_elec)?  It must not
+  // leave the operator's class (real / imaginary) nor, in the compressed pair space,
+  // break the i<->j symmetry.  If not, sigma.cu adds the one-body term with its own kernel.
+  op->absorb_ok = false;
+  if (op->has_h2) {
     bool ok = true;
-    for (int p = 0; p < npair && ok; ++p) ok = (h_h1p[2 * p + part_zero] == 0.0);
+    if (op->kind != FQEB_OP_COMPLEX) {
+      const int part_zero = op->kind == FQEB_OP_IMAG ? 0 : 1;  // component that must vanish
+      for (int p = 0; p < npair && ok; ++p) ok = (h_h1p[2 * p + part_zero] == 0.0);
+    }
     if (op->sym)
       for (int i = 0; i < norb && ok; ++i)
         for (int j = 0; j < i && ok; ++j)
           ok = h_h1p[2 * (i * norb + j)] == h_h1p[2 * (j * norb + i)] &&
                h_h1p[2 * (i * norb + j) + 1] == h_h1p[2 * (j * norb + i) + 1];
-    op->fuse_ok = ok;
+    op->absorb_ok = ok;
   }
-  if (op->fuse_ok) {
+  // fused gather+contraction (opt-in): additionally needs a single row block
+  op->fuse_ok = op->absorb_ok && fused_shape_ok(op);
+  if (op->absorb_ok) {
     op->h_h1p = (double *)malloc(sizeof(double) * 2 * npair);
     op->h_h2p = (double *)malloc(sizeof(double) * 2 * (size_t)npair * npair);
     if (!op->h_h1p || !op->h_h2p) {
@@ -1185,13 +1194,11 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
 }
 
 namespace fqeb {
-// Operand of the fused kernel for a sector with n_elec electrons: the real/imaginary
-// part of h2' in the operator's pair space with the one-body term absorbed,
-//   A[c, d] += h1'[pair(c)] / n_elec   for every diagonal pair d = (k, k),
-// which is exact on a fixed-particle-number sector because sum_k E_kk = n_elec.
-// Built on first use and cached per n_elec.
-int fused_operand(const fqeb_op *op, int n_elec, const double **d_A) {
-  FQEB_REQUIRE(op->fuse_ok && n_elec > 0, "fused_operand: operator not fusable");
+// Contraction operand for a sector with n_elec electrons: h2' in the operator's pair space
+// (same layout as fqeb_op::d_A) with the one-body term absorbed into the diagonal-pair
+// columns.  Built on first use and cached per n_elec.
+int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A) {
+  FQEB_REQUIRE(op->absorb_ok && n_elec > 0, "absorbed_operand: one-body term not absorbable");
   auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
   auto it = cache->find(n_elec);
   if (it != cache->end()) {
@@ -1199,23 +1206,34 @@ int fused_operand(const fqeb_op *op, int n_elec, const double **d_A) {
     return FQEB_OK;
   }
   const int norb = op->norb, npair = norb * norb, np = op->np;
-  const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
   auto pair_of = [&](int c) {
     if (!op->sym) return c;
     int i = 0;
     while ((i + 1) * (i + 2) / 2 <= c) ++i;
     return i * norb + (c - i * (i + 1) / 2);
   };
+  auto elem = [&](int c, int d, int part) {
+    const int ij = pair_of(c), kl = pair_of(d);
+    double v = op->h_h2p[2 * ((size_t)ij * npair + kl) + part];
+    if (kl / norb == kl % norb) v += op->h_h1p[2 * ij + part] / (double)n_elec;
+    return v;
+  };
   std::vector<double> a((size_t)op->Mp * op->Kp, 0.0);
-  for (int c = 0; c < np; ++c) {
-    const int ij = pair_of(c);
-    const double h1 = op->h_h1p[2 * ij + off] / (double)n_elec;
-    for (int d = 0; d < np; ++d) {
-      const int kl = pair_of(d);
-      double v = op->h_h2p[2 * ((size_t)ij * npair + kl) + off];
-      if (kl / norb == kl % norb) v += h1;
-      a[(size_t)c * op->Kp + d] = v;
+  if (op->kind == FQEB_OP_COMPLEX) {
+    for (int c = 0; c < np; ++c) {
+      const int rre = (c / 8) * 16 + (c % 8), rim = rre + 8;
+      for (int d = 0; d < np; ++d) {
+        const double re = elem(c, d, 0), im = elem(c, d, 1);
+        a[(size_t)rre * op->Kp + 2 * d] = re;
+        a[(size_t)rre * op->Kp + 2 * d + 1] = -im;
+        a[(size_t)rim * op->Kp + 2 * d] = im;
+        a[(size_t)rim * op->Kp + 2 * d + 1] = re;
+      }
     }
+  } else {
+    const int off = op->kind == FQEB_OP_IMAG ? 1 : 0;
+    for (int c = 0; c < np; ++c)
+      for (int d = 0; d < np; ++d) a[(size_t)c * op->Kp + d] = elem(c, d, off);
   }
   double *dev = nullptr;
   FQEB_CUDA(cudaMalloc(&dev, sizeof(double) * a.size()));
@@ -1261,5 +1279,6 @@ extern "C" int fqeb_contract(const fqeb_op *op, const double *d_dvec, int64_t ld
   int rc = require_device();
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(op && d_dvec && d_evec, "fqeb_contract: NULL argument");
-  return launch_contract(op, d_dvec, ldd, d_evec, lde, ncols, ij0, ij1, (cudaStream_t)stream);
+  return launch_contract(op, nullptr, d_dvec, ldd, d_evec, lde, ncols, ij0, ij1,
+                         (cudaStream_t)stream);
 }

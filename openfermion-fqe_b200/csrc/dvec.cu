@@ -191,6 +191,73 @@ k_make_dvec(int npair_total, int64_t lena, int64_t lenb, const int32_t *__restri
   }
 }
 
+// exact sign flip: XOR the sign bit of the map entry into the double
+__device__ __forceinline__ double flip_sign(double v, int t) {
+  return __hiloint2double(__double2hiint(v) ^ (t & (int)0x80000000), __double2loint(v));
+}
+
+// Single-source gather: D row (c - c0) of table row c is
+//     D[a, b] = sgn(ta) C[|ta|-1, b] + sgn(tb) C[a, |tb|-1],   ta = mapT_a[a][c], tb = map_b[c][b]
+// with either the plain adjoint map (ntab = norb^2, one row per ij) or the merged map of
+// the compressed pair space (ntab = norb(norb+1)/2, fqeb_graph::d_smap), in which
+// D_c = D[ij] + D[ji] has at most one alpha and one beta source per element.
+// One CTA = one alpha row x 256 beta strings; ta is resolved once per CTA into shared memory.
+// U table rows per trip; the beta-map entries of trip n+1 are requested before the C elements
+// of trip n are consumed (one global round trip per trip instead of two dependent ones).
+template <int U>
+__global__ void __launch_bounds__(kTB, 3)
+k_gather(int ntab, int64_t lenb, const int32_t *__restrict__ mapT_a,
+         const int32_t *__restrict__ map_b, const double2 *__restrict__ coeff,
+         double2 *__restrict__ dvec, int64_t ldd, int64_t row0, int nbt, int c0, int c1) {
+  extern __shared__ int s_ta[];
+  const int64_t tile = blockIdx.x;
+  const int64_t r = tile / nbt;
+  const int64_t a = row0 + r;
+  const int n = c1 - c0;
+  for (int c = threadIdx.x; c < n; c += kTB) s_ta[c] = mapT_a[a * (int64_t)ntab + c0 + c];
+  __syncthreads();
+  const int64_t b = (tile % nbt) * kTB + threadIdx.x;
+  if (b >= lenb) return;
+  const double2 *__restrict__ crow = coeff + a * lenb;
+  const double2 *__restrict__ ccol = coeff + b;
+  const int32_t *__restrict__ mb = map_b + (int64_t)c0 * lenb + b;
+  double2 *__restrict__ dout = dvec + r * lenb + b;
+  const int nfull = n - n % U;
+  int tb[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) tb[u] = (u < nfull) ? ldg_int(mb + (int64_t)u * lenb) : 0;
+  for (int c = 0; c < nfull; c += U) {
+    int ta[U];
+    double2 va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ta[u] = s_ta[c + u];
+      va[u] = ldg_c128_if(ta[u] != 0, ccol + (int64_t)(abs(ta[u]) - 1) * lenb);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) vb[u] = ldg_c128_if(tb[u] != 0, crow + (abs(tb[u]) - 1));
+    int nb[U];
+    const bool more = (c + U < nfull);
+#pragma unroll
+    for (int u = 0; u < U; ++u) nb[u] = more ? ldg_int(mb + (int64_t)(c + U + u) * lenb) : 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // streaming stores: D is far larger than L2 and is read back only by the next kernel
+      __stcs(dout + (int64_t)(c + u) * ldd,
+             make_double2(flip_sign(va[u].x, ta[u]) + flip_sign(vb[u].x, tb[u]),
+                          flip_sign(va[u].y, ta[u]) + flip_sign(vb[u].y, tb[u])));
+      tb[u] = nb[u];
+    }
+  }
+  for (int c = nfull; c < n; ++c) {
+    const int ta = s_ta[c], t = mb[(int64_t)c * lenb];
+    const double2 va = ldg_c128_if(ta != 0, ccol + (int64_t)(abs(ta) - 1) * lenb);
+    const double2 vb = ldg_c128_if(t != 0, crow + (abs(t) - 1));
+    __stcs(dout + (int64_t)c * ldd, make_double2(flip_sign(va.x, ta) + flip_sign(vb.x, t),
+                                                 flip_sign(va.y, ta) + flip_sign(vb.y, t)));
+  }
+}
+
 // Scatter, by target.  One CTA = one target alpha row x 256 beta strings.
 //   alpha part: the lk_a non-vanishing excitations of row x are filtered ONCE per CTA
 //               against the chunk's row range (ordered, deterministic compaction into
@@ -383,6 +450,29 @@ int launch_one_body(const fqeb_graph *g, const double *d_coeff, const double *d_
   return FQEB_OK;
 }
 
+// D rows for the table rows [c0, c1): the plain pair space (sym = false, table row = ij) or
+// the compressed one (sym = true, table row = i(i+1)/2 + j)
+int launch_gather(const fqeb_graph *g, bool sym, const double *d_coeff, double *d_dvec,
+                  int64_t ldd, int64_t row0, int64_t nrows, int c0, int c1, cudaStream_t st) {
+  const int ntab = sym ? g->norb * (g->norb + 1) / 2 : g->norb * g->norb;
+  const int64_t lena = g->len[0], lenb = g->len[1];
+  FQEB_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= lena,
+               "make_dvec: rows [%lld,+%lld) outside [0,%lld)", (long long)row0, (long long)nrows,
+               (long long)lena);
+  FQEB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= ntab, "make_dvec: pair slice [%d,%d) invalid", c0, c1);
+  FQEB_REQUIRE(ldd >= nrows * lenb, "make_dvec: ldd=%lld < nrows*lenb", (long long)ldd);
+  if (nrows == 0 || c0 == c1) return FQEB_OK;
+  const int nbt = (int)((lenb + kTB - 1) / kTB);
+  const int64_t tiles = nrows * nbt;
+  FQEB_REQUIRE(tiles < (1ll << 31), "make_dvec: chunk too large for one launch");
+  const size_t smem = sizeof(int) * (size_t)(c1 - c0);
+  k_gather<4><<<(unsigned)tiles, kTB, smem, st>>>(
+      ntab, lenb, sym ? g->d_smapT[0] : g->d_amapT[0], sym ? g->d_smap[1] : g->d_amap[1],
+      (const double2 *)d_coeff, (double2 *)d_dvec, ldd, row0, nbt, c0, c1);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
 // pairs == nullptr: identity pair list of the graph (D row c <-> pair c), np_eff = norb^2
 int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec, int64_t ldd,
                      int64_t row0, int64_t nrows, int ij0, int ij1, const int32_t *d_pairs,
@@ -416,10 +506,11 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
         npair_full, lena, lenb, g->d_amapT[0], g->d_amap[1], c, d, ldd, row0, nbt, ij0, ij1,   \
         d_pairs, h1, sig);                                                                     \
   } while (0)
-  if (d && h1) FQEB_LAUNCH_DVEC(true, true);
-  else if (d) FQEB_LAUNCH_DVEC(true, false);
-  else if (h1) FQEB_LAUNCH_DVEC(false, true);
-  else return FQEB_OK;
+  // D itself is produced by launch_gather; this launcher only serves the one-body
+  // accumulation over a pair slice
+  FQEB_REQUIRE(d == nullptr && h1 != nullptr && sig != nullptr,
+               "make_dvec: one-body accumulation needs h1 and sigma, and no D buffer");
+  FQEB_LAUNCH_DVEC(false, true);
 #undef FQEB_LAUNCH_DVEC
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
@@ -463,8 +554,8 @@ extern "C" int fqeb_make_dvec(const fqeb_graph *g, const double *d_coeff, double
   int rc = fqeb::require_device();
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(g && d_coeff && d_dvec, "fqeb_make_dvec: NULL argument");
-  return fqeb::launch_make_dvec(g, d_coeff, d_dvec, ldd, row0, nrows, ij0, ij1, nullptr, 0,
-                                nullptr, nullptr, (cudaStream_t)stream);
+  return fqeb::launch_gather(g, false, d_coeff, d_dvec, ldd, row0, nrows, ij0, ij1,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int fqeb_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde,

@@ -65,6 +65,11 @@ struct fqeb_graph {
   // adjoint map: amap[ij][x] = sign*(y+1) with a^+_j a_i |x> = sign |y>  (ij = i*norb+j)
   int32_t *d_amap[2];      // [norb*norb][len]
   int32_t *d_amapT[2];     // [len][norb*norb]
+  // merged map of the compressed pair space c = i(i+1)/2 + j (i >= j): the entry of ij or
+  // of ji, whichever is non-zero (for i != j at most one is: i occupied and j empty, or the
+  // reverse), so that D_c = D[ij] + D[ji] is a single-source gather
+  int32_t *d_smap[2];      // [norb(norb+1)/2][len]
+  int32_t *d_smapT[2];     // [len][norb(norb+1)/2]
   // compact lists of the lk = nele*(norb-nele+1) non-vanishing adjoint-map entries of
   // every string, as int2 (ij, sign*(y+1)), ascending ij:
   int lk[2];
@@ -95,6 +100,7 @@ struct fqeb_op {
   // fused gather+contraction (dgemm.cu k_sigma_fused): usable when one CTA covers the
   // whole row space and the one-body term can be folded into the operand
   bool fuse_ok;
+  bool absorb_ok;          // one-body term can be folded into the contraction operand
   double *h_h1p, *h_h2p;   // host copies (complex, interleaved) for per-sector operands
   void *fused_cache;       // std::map<int, double*>*: n_elec -> device operand with h1 absorbed
 };

@@ -110,6 +110,23 @@ __global__ void k_build_maps(int norb, int64_t len,
   amapT[x * (int64_t)(norb * norb) + p] = val;
 }
 
+// merged map of the compressed pair space (see fqeb_graph::d_smap)
+__global__ void k_build_symmaps(int norb, int64_t len, const int32_t *__restrict__ amapT,
+                                int32_t *__restrict__ smap, int32_t *__restrict__ smapT) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= len) return;
+  const int npc = norb * (norb + 1) / 2;
+  const int32_t *row = amapT + x * (int64_t)(norb * norb);
+  int c = 0;
+  for (int i = 0; i < norb; ++i)
+    for (int j = 0; j <= i; ++j, ++c) {
+      int v = row[i * norb + j];
+      if (v == 0 && i != j) v = row[j * norb + i];
+      smap[(int64_t)c * len + x] = v;
+      smapT[x * (int64_t)npc + c] = v;
+    }
+}
+
 // compact the non-zero adjoint-map entries of each string (exactly lk of them)
 __global__ void k_build_clists(int npair, int64_t len, int lk, const int32_t *__restrict__ amapT,
                                int2 *__restrict__ clistT, int2 *__restrict__ clist) {
@@ -147,6 +164,12 @@ static int build_spin(fqeb_graph *g, int spin, const uint64_t *d_binom) {
     dim3 grid(blocks, npair);
     k_build_maps<<<grid, threads>>>(norb, len, g->d_str[spin], g->d_Z[spin], g->d_amap[spin],
                                     g->d_amapT[spin]);
+    FQEB_CHECK_LAUNCH();
+    const size_t sbytes = sizeof(int32_t) * (size_t)(norb * (norb + 1) / 2) * len;
+    FQEB_CUDA(cudaMalloc(&g->d_smap[spin], sbytes));
+    FQEB_CUDA(cudaMalloc(&g->d_smapT[spin], sbytes));
+    k_build_symmaps<<<blocks, threads>>>(norb, len, g->d_amapT[spin], g->d_smap[spin],
+                                         g->d_smapT[spin]);
     FQEB_CHECK_LAUNCH();
   }
   const int lk = nele * (norb - nele + 1);
@@ -223,6 +246,8 @@ extern "C" int fqeb_graph_create(int norb, int nalpha, int nbeta, fqeb_graph **o
       g->d_str[1] = g->d_str[0];
       g->d_amap[1] = g->d_amap[0];
       g->d_amapT[1] = g->d_amapT[0];
+      g->d_smap[1] = g->d_smap[0];
+      g->d_smapT[1] = g->d_smapT[0];
       g->lk[1] = g->lk[0];
       g->d_clistT[1] = g->d_clistT[0];
       g->d_clist[1] = g->d_clist[0];
@@ -272,6 +297,8 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
     if (g->d_str[s]) cudaFree(g->d_str[s]);
     if (g->d_amap[s]) cudaFree(g->d_amap[s]);
     if (g->d_amapT[s]) cudaFree(g->d_amapT[s]);
+    if (g->d_smap[s]) cudaFree(g->d_smap[s]);
+    if (g->d_smapT[s]) cudaFree(g->d_smapT[s]);
     if (g->d_clistT[s]) cudaFree(g->d_clistT[s]);
     if (g->d_clist[s]) cudaFree(g->d_clist[s]);
   }

@@ -5,9 +5,13 @@
 // the reference's Python branch spells out at fqe_data.py:653-657):
 //
 //     D[ij]  = E_ij C                      gather        (dvec.cu,  HBM-bound)
-//     sigma += sum_ij h1'[ij] D[ij]        fused into the gather
 //     E[kl]  = sum_ij h2'[kl,ij] D[ij]     DMMA GEMM     (dgemm.cu, FP64-bound)
 //     sigma += sum_kl E_kl^T E[kl]         scatter       (dvec.cu,  HBM-bound)
+//
+// The one-body term sum_ij h1'[ij] D[ij] costs nothing: on a sector with n_elec electrons
+// sum_k D[kk] = n_elec C, so h1'[kl]/n_elec is added to the operand's diagonal-pair columns
+// (absorbed_operand, dgemm.cu).  Operators whose h1' would leave the class of h2' (e.g. a
+// complex h1' next to a real h2') get a separate accumulation pass instead.
 //
 // D and E are norb^2 times larger than C (678 GB at norb=16), so the determinant
 // index is streamed in chunks of alpha rows through a caller-provided workspace;
@@ -34,9 +38,12 @@ int launch_one_body(const fqeb_graph *g, const double *d_coeff, const double *d_
 int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
                  int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde, int ij0,
                  int ij1, cudaStream_t st);
-int fused_operand(const fqeb_op *op, int n_elec, const double **d_A);
-int launch_contract(const fqeb_op *op, const double *d_dvec, int64_t ldd, double *d_evec,
-                    int64_t lde, int64_t ncols, int ij0, int ij1, cudaStream_t st);
+int launch_gather(const fqeb_graph *g, bool sym, const double *d_coeff, double *d_dvec,
+                  int64_t ldd, int64_t row0, int64_t nrows, int c0, int c1, cudaStream_t st);
+int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A);
+int launch_contract(const fqeb_op *op, const double *d_A, const double *d_dvec, int64_t ldd,
+                    double *d_evec, int64_t lde, int64_t ncols, int ij0, int ij1,
+                    cudaStream_t st);
 int dvec_rows_padded(const fqeb_op *op, int nij);
 int dvec_rows_zeroed(const fqeb_op *op, int nij);
 
@@ -186,7 +193,7 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   const int nij = ij1 - ij0;
   if (L.fused) {
     const double *d_A = nullptr;
-    rc = fused_operand(op, g->nele[0] + g->nele[1], &d_A);
+    rc = absorbed_operand(op, g->nele[0] + g->nele[1], &d_A);
     if (rc != FQEB_OK) return rc;
     double *d_e = (double *)d_workspace;
     for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
@@ -212,17 +219,26 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
     FQEB_CUDA(cudaMemsetAsync(d_dvec + 2 * (size_t)nij * L.ldd, 0,
                               sizeof(double) * 2 * (size_t)(zrows - nij) * L.ldd, st));
   }
+  const int n_elec = g->nele[0] + g->nele[1];
+  const bool absorb = op->absorb_ok && n_elec > 0;
+  const double *d_A = nullptr;
+  if (absorb) {
+    rc = absorbed_operand(op, n_elec, &d_A);
+    if (rc != FQEB_OK) return rc;
+  }
   for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
     const int64_t nr = (row1 - a0) < rows_chunk ? (row1 - a0) : rows_chunk;
     {
       PhaseTimer t(0, st);
-      rc = launch_make_dvec(g, d_coeff, d_dvec, L.ldd, a0, nr, ij0, ij1, op->d_pairs, op->np,
-                            op->d_h1, d_sigma, st);
+      rc = launch_gather(g, op->sym, d_coeff, d_dvec, L.ldd, a0, nr, ij0, ij1, st);
+      if (rc == FQEB_OK && !absorb)
+        rc = launch_make_dvec(g, d_coeff, nullptr, 0, a0, nr, ij0, ij1, op->d_pairs, op->np,
+                              op->d_h1, d_sigma, st);
     }
     if (rc != FQEB_OK) return rc;
     {
       PhaseTimer t(1, st);
-      rc = launch_contract(op, d_dvec, L.ldd, d_evec, L.ldd, nr * lenb, ij0, ij1, st);
+      rc = launch_contract(op, d_A, d_dvec, L.ldd, d_evec, L.ldd, nr * lenb, ij0, ij1, st);
     }
     if (rc != FQEB_OK) return rc;
     {
