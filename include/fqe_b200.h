@@ -206,6 +206,53 @@ int fqeb_dc_evolve(const fqeb_graph *g, const double *h_diag,
                    const double *h_array, double *d_coeff, void *stream);
 
 /* ------------------------------------------------------------------------
+ * 8f-1  orbital rotation by column operators, one-body diagonal apply / evolve
+ * fqeb_apply_columns replaces lm_apply_array1_column_alpha
+ * (lib/fqe_data.h:71-82, lib/fqe_data.c:305-347) as looped over icol by
+ * FqeData._apply_columns_recursive_alpha (fqe_data.py:1476-1504): for
+ * icol = 0..norb-1 in order, C <- (1 + sum_i mat[i,icol] a^+_i a_icol) C on one
+ * spin (0 = alpha rows, 1 = beta columns; the reference transposes C for beta,
+ * fqe_data.py:1506-1535), in place.  h_mat: complex128[norb,norb] row-major
+ * (host), the `process_matrix` output of Wavefunction.transform
+ * (wavefunction.py:889-909).
+ * fqeb_apply_diagonal / fqeb_evolve_diagonal replace apply_diagonal_inplace /
+ * evolve_diagonal_inplace (lib/fqe_data.c:1320-1383; fqe_data.py:153-261):
+ * C[a,b] *= A[a] + B[b]  resp.  C[a,b] *= exp(A[a]) * exp(B[b]) with
+ * A[a] = sum_{i in a} aarray[i], B[b] = sum_{i in b} barray[i];
+ * h_aarray, h_barray: complex128[norb] (host).
+ * ------------------------------------------------------------------------ */
+int fqeb_apply_columns(const fqeb_graph *g, int spin, const double *h_mat,
+                       double *d_coeff, void *stream);
+int fqeb_apply_diagonal(const fqeb_graph *g, const double *h_aarray,
+                        const double *h_barray, double *d_coeff, void *stream);
+int fqeb_evolve_diagonal(const fqeb_graph *g, const double *h_aarray,
+                         const double *h_barray, double *d_coeff, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 8f-2  individual n-body operators
+ * fqeb_nbody_accumulate replaces make_mapping_each (lib/fci_graph.h:64-70,
+ * lib/fci_graph.c:223-264) + apply_individual_nbody1_accumulate
+ * (lib/fqe_data.h:150-158, lib/fqe_data.c:1157-1182) as called by
+ * FqeData.apply_individual_nbody_accumulate (fqe_data.py:1590-1653):
+ *   out[ta,tb] += z * pa * pb * in[sa,sb]
+ * for the spin-conserving operator  prod a+_{daga} prod a_{undaga} (alpha, na
+ * of each) x prod a+_{dagb} prod a_{undagb} (beta, nb of each); operators act
+ * right to left in list order.  d_in and d_out must differ.
+ * fqeb_sparse_scale replaces evaluate_map_each + sparse_scale
+ * (lib/fqe_data.c:1417-1440, 1265-1278; FqeData.apply_cos_inplace and
+ * evolve_inplace_individual_nbody_trivial, fqe_data.py:2385-2433, 2497-2580):
+ * C[a,b] *= f for the alpha strings with every orbital of bit mask a_occ occupied
+ * and every orbital of a_emp empty, and likewise for beta.
+ * ------------------------------------------------------------------------ */
+int fqeb_nbody_accumulate(const fqeb_graph *g, double zr, double zi,
+                          const int *daga, const int *undaga, int na,
+                          const int *dagb, const int *undagb, int nb,
+                          const double *d_in, double *d_out, void *stream);
+int fqeb_sparse_scale(const fqeb_graph *g, uint64_t a_occ, uint64_t a_emp,
+                      uint64_t b_occ, uint64_t b_emp, double fr, double fi,
+                      double *d_coeff, void *stream);
+
+/* ------------------------------------------------------------------------
  * a15  BLAS-1 on coefficient vectors (n complex elements)
  * replaces FqeData.ax_plus_y / scale / norm and util.vdot
  * (fqe_data.py:2620-2632, 2745-2751, 2701-2707; util.py:506-530).

@@ -953,7 +953,6 @@ int launch_contract(const fqeb_op *op, const double *d_A, const double *d_dvec, 
   const bool cplx = op->kind == FQEB_OP_COMPLEX;
   const int nij = ij1 - ij0;
   const int k_valid = cplx ? 2 * nij : nij;
-  const int nk = (k_valid + KSTEP - 1) / KSTEP;
   const int a_col0 = cplx ? 2 * ij0 : ij0;
   FQEB_REQUIRE(a_col0 + round_up(k_valid, KSTEP_MAX) <= op->Kp,
                "contract: operator padding too small");

@@ -54,6 +54,21 @@ constexpr int kMaxOrb = 63;  // as the reference C path (settings.py c_string_ma
 }  // namespace fqeb
 
 // ---- handle definitions -----------------------------------------------------
+// Knowles-Handy address of a string: sum_k Z[k, o_k] over its occupied orbitals o_0 < o_1 < ...
+// (reference fci_graph.py:401-419, lib/fci_graph.c:123-134)
+__device__ __forceinline__ int fqeb_string_address(uint64_t s, const int32_t *__restrict__ z,
+                                               int norb) {
+  int addr = 0, k = 0;
+  while (s) {
+    const int bit = __ffsll((long long)s) - 1;
+    s &= s - 1;
+    addr += z[k * norb + bit];
+    ++k;
+  }
+  return addr;
+}
+
+
 struct fqeb_graph {
   int norb, nele[2];
   int64_t len[2];
@@ -78,6 +93,9 @@ struct fqeb_graph {
   double *d_small;         // scratch for small operator uploads (diag, v, ...)
   size_t small_bytes;
   double *d_sterm[2];      // per-string diagonal-Coulomb terms, complex [len]
+  // ordered lists of the strings with orbital icol occupied / empty, built on first use by
+  // the column-rotation kernels (rotate.cu): [norb][C(norb-1,nele-1)] / [norb][C(norb-1,nele)]
+  int32_t *d_occ[2], *d_unocc[2];
   int32_t *d_pairs_id;     // identity pair list [norb^2][2] = (ij, -1)
   int32_t *d_rowmap_id;    // identity row map [norb^2]
 };

@@ -47,18 +47,6 @@ static void host_z_matrix(const uint64_t *binom, int norb, int nele, int32_t *z)
   for (int l = nele; l <= norb; ++l) z[(nele - 1) * norb + (l - 1)] = l - nele;
 }
 
-__device__ __forceinline__ int string_address(uint64_t s, const int32_t *__restrict__ z,
-                                               int norb) {
-  int addr = 0, k = 0;
-  while (s) {
-    const int bit = __ffsll((long long)s) - 1;
-    s &= s - 1;
-    addr += z[k * norb + bit];
-    ++k;
-  }
-  return addr;
-}
-
 // one thread per rank r in ascending-integer order
 __global__ void k_build_strings(int nele, int norb, int64_t len,
                                 const uint64_t *__restrict__ binom,
@@ -77,7 +65,7 @@ __global__ void k_build_strings(int nele, int norb, int64_t len,
     r -= binom[cc * 65 + t];
     c = cc;
   }
-  out[string_address(s, z, norb)] = s;
+  out[fqeb_string_address(s, z, norb)] = s;
 }
 
 // adjoint-map entry for pair index p = i*norb + j and string x:
@@ -102,7 +90,7 @@ __global__ void k_build_maps(int norb, int64_t len,
       const uint64_t between = ((1ull << hi) - 1) & ~((2ull << lo) - 1);
       const int par = __popcll(s & between) & 1;
       const uint64_t t = (s & ~bi) | bj;
-      const int y = string_address(t, z, norb);
+      const int y = fqeb_string_address(t, z, norb);
       val = par ? -(y + 1) : (y + 1);
     }
   }
@@ -299,6 +287,8 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
     if (g->d_amapT[s]) cudaFree(g->d_amapT[s]);
     if (g->d_smap[s]) cudaFree(g->d_smap[s]);
     if (g->d_smapT[s]) cudaFree(g->d_smapT[s]);
+    if (g->d_occ[s]) cudaFree(g->d_occ[s]);
+    if (g->d_unocc[s]) cudaFree(g->d_unocc[s]);
     if (g->d_clistT[s]) cudaFree(g->d_clistT[s]);
     if (g->d_clist[s]) cudaFree(g->d_clist[s]);
   }

@@ -5,7 +5,8 @@ from typing import List, Optional, Tuple
 import numpy
 
 from fqe_b200 import wavefunction as _wfn
-from fqe_b200.hamiltonians import diagonal_coulomb, restricted_hamiltonian
+from fqe_b200.hamiltonians import (diagonal_coulomb, diagonal_hamiltonian, restricted_hamiltonian,
+                                   sparse_hamiltonian)
 
 
 def Wavefunction(param: List[List[int]], broken=None) -> '_wfn.Wavefunction':
@@ -26,6 +27,16 @@ def get_restricted_hamiltonian(tensors: Tuple[numpy.ndarray, ...], e_0: complex 
 def get_diagonalcoulomb_hamiltonian(h2e: numpy.ndarray, e_0: complex = 0. + 0.j):
     """(_fqe_control.py:495-508)"""
     return diagonal_coulomb.DiagonalCoulomb(h2e, e_0=e_0)
+
+
+def get_diagonal_hamiltonian(hdiag: numpy.ndarray, e_0: complex = 0. + 0.j):
+    """(_fqe_control.py:511-523)"""
+    return diagonal_hamiltonian.Diagonal(hdiag, e_0=e_0)
+
+
+def get_sparse_hamiltonian(operators, conserve_spin: bool = True, e_0: complex = 0. + 0.j):
+    """(_fqe_control.py:577-597); ``operators``: FermionOperator-like, terms mapping or string"""
+    return sparse_hamiltonian.SparseHamiltonian(operators, conserve_spin=conserve_spin, e_0=e_0)
 
 
 def apply(ops, wfn: '_wfn.Wavefunction') -> '_wfn.Wavefunction':

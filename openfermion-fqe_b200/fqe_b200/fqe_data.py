@@ -530,3 +530,148 @@ class FqeData:
 
     def evolve_diagonal_coulomb(self, diag, array, inplace: bool = False) -> torch.Tensor:
         return self._dc("fqeb_dc_evolve", diag, array, inplace)
+
+    # ---- one-body diagonal operators (fqe_data.py:153-261) -----------------------------
+    def _diag_arrays(self, array) -> Tuple[numpy.ndarray, numpy.ndarray]:
+        array = _host_c128(array)
+        norb = self.norb()
+        if array.size == 2 * norb:
+            return numpy.ascontiguousarray(array[:norb]), numpy.ascontiguousarray(array[norb:])
+        if array.size != norb:
+            raise ValueError('Non-diagonal array passed into a diagonal operator')
+        return array, array
+
+    def apply_diagonal_inplace(self, array) -> None:
+        """C[a,b] *= sum_{i in a} array[i] + sum_{i in b} array[i]  (fqe_data.py:153-201);
+        a 2*norb array holds separate alpha and beta values."""
+        _require_cuda()
+        aarr, barr = self._diag_arrays(array)
+        _lib.call("fqeb_apply_diagonal", self._core.handle, aarr.ctypes.data, barr.ctypes.data,
+                  self._check_coeff(self.coeff).data_ptr(), _stream())
+
+    def evolve_diagonal(self, array, inplace: bool = False) -> torch.Tensor:
+        """C[a,b] *= exp(sum_{i in a} array[i]) exp(sum_{i in b} array[i])
+        (fqe_data.py:203-261); ``array`` is already multiplied by -i*t."""
+        _require_cuda()
+        aarr, barr = self._diag_arrays(array)
+        data = self.coeff if inplace else self.coeff.clone()
+        _lib.call("fqeb_evolve_diagonal", self._core.handle, aarr.ctypes.data, barr.ctypes.data,
+                  self._check_coeff(data).data_ptr(), _stream())
+        return data
+
+    # ---- individual n-body operators (fqe_data.py:1558-1653, 2385-2580) --------------------
+    @staticmethod
+    def _op_arrays(dag, undag, norb: int):
+        if len(dag) != len(undag):
+            raise NotImplementedError("only spin- and number-conserving individual operators "
+                                      "(equal numbers of creators and annihilators per spin)")
+        for o in list(dag) + list(undag):
+            if o < 0 or o >= norb:
+                raise ValueError("orbital index out of range")
+        return (numpy.ascontiguousarray(dag, dtype=numpy.int32),
+                numpy.ascontiguousarray(undag, dtype=numpy.int32))
+
+    def apply_individual_nbody(self, coeff: complex, daga, undaga, dagb, undagb) -> 'FqeData':
+        """coeff * prod a+_{daga} prod a_{undaga} prod a+_{dagb} prod a_{undagb} |self>"""
+        out = FqeData(self.nalpha(), self.nbeta(), self.norb(), self._core)
+        out.coeff.zero_()
+        out.apply_individual_nbody_accumulate(coeff, self, daga, undaga, dagb, undagb)
+        return out
+
+    def apply_individual_nbody_accumulate(self, coeff: complex, idata: 'FqeData', daga, undaga,
+                                          dagb, undagb) -> None:
+        """self += coeff * (individual operator) |idata>  (fqe_data.py:1590-1653)"""
+        _require_cuda()
+        da, ua = self._op_arrays(daga, undaga, self.norb())
+        db, ub = self._op_arrays(dagb, undagb, self.norb())
+        if idata.coeff.data_ptr() == self.coeff.data_ptr():
+            raise ValueError("input and output of an individual n-body apply must differ")
+        coeff = complex(coeff)
+        _lib.call("fqeb_nbody_accumulate", self._core.handle, coeff.real, coeff.imag,
+                  da.ctypes.data, ua.ctypes.data, len(da), db.ctypes.data, ub.ctypes.data, len(db),
+                  self._check_coeff(idata.coeff).data_ptr(),
+                  self._check_coeff(self.coeff).data_ptr(), _stream())
+
+    def _sparse_scale(self, factor: complex, opa, oha, opb, ohb) -> None:
+        def mask(ops):
+            m = 0
+            for o in ops:
+                m |= 1 << int(o)
+            return m
+        factor = complex(factor)
+        _lib.call("fqeb_sparse_scale", self._core.handle, mask(opa), mask(oha), mask(opb),
+                  mask(ohb), factor.real, factor.imag, self._check_coeff(self.coeff).data_ptr(),
+                  _stream())
+
+    def apply_cos_inplace(self, time: float, ncoeff: complex, opa, oha, opb, ohb) -> None:
+        """C *= cos(t |ncoeff|) on the determinants with opa/opb occupied and oha/ohb empty
+        (fqe_data.py:2548-2580)"""
+        _require_cuda()
+        self._sparse_scale(math.cos(time * abs(ncoeff)), opa, oha, opb, ohb)
+
+    def evolve_inplace_individual_nbody_trivial(self, time: float, coeff: complex, opa,
+                                                opb) -> None:
+        """exp(-i t (T + T^+)) for T = coeff * (product of number operators), in place
+        (fqe_data.py:2385-2433); coeff includes the parity due to sorting."""
+        _require_cuda()
+        n_a, n_b = len(opa), len(opb)
+        coeff = complex(coeff) * (-1)**(n_a * (n_a - 1) // 2 + n_b * (n_b - 1) // 2)
+        factor = numpy.exp(-time * numpy.real(coeff) * 2.j)
+        self._sparse_scale(factor, opa, [], opb, [])
+
+    def evolve_individual_nbody_nontrivial(self, time: float, coeff: complex, daga, undaga, dagb,
+                                           undagb) -> 'FqeData':
+        """exp(-i t (T + T^+)) |self> for an individual spin-conserving T with T^2 = 0
+        (fqe_data.py:2435-2513):  -1 + cos(t sqrt(T T^+)) + cos(t sqrt(T^+ T))
+        - i T sin(t sqrt(T^+ T))/sqrt(T^+ T) - i T^+ sin(t sqrt(T T^+))/sqrt(T T^+)."""
+        _require_cuda()
+
+        def isolate_number_operators(dag, undag, dagwork, undagwork, number) -> int:
+            par = 0
+            for current in dag:
+                if current in undag:
+                    index1 = dagwork.index(current)
+                    index2 = undagwork.index(current)
+                    par += len(dagwork) - (index1 + 1) + index2
+                    dagwork.remove(current)
+                    undagwork.remove(current)
+                    number.append(current)
+            return par
+
+        daga, undaga, dagb, undagb = list(daga), list(undaga), list(dagb), list(undagb)
+        dagworka, undagworka = list(daga), list(undaga)
+        dagworkb, undagworkb = list(dagb), list(undagb)
+        numbera: list = []
+        numberb: list = []
+        parity = isolate_number_operators(daga, undaga, dagworka, undagworka, numbera)
+        parity += isolate_number_operators(dagb, undagb, dagworkb, undagworkb, numberb)
+        ncoeff = coeff * (-1)**parity
+        absol = numpy.absolute(ncoeff)
+        sinfactor = numpy.sin(time * absol) / absol
+
+        out = FqeData(self.nalpha(), self.nbeta(), self.norb(), self._core)
+        out.coeff.copy_(self.coeff)
+        out.apply_cos_inplace(time, ncoeff, numbera + dagworka, undagworka, numberb + dagworkb,
+                              undagworkb)
+        out.apply_cos_inplace(time, ncoeff, numbera + undagworka, dagworka, numberb + undagworkb,
+                              dagworkb)
+        phase = (-1)**((len(daga) + len(undaga)) * (len(dagb) + len(undagb)))
+        work_cof = numpy.conj(coeff) * phase * (-1.0j)
+        out.apply_individual_nbody_accumulate(work_cof * sinfactor, self, undaga, daga, undagb,
+                                              dagb)
+        out.apply_individual_nbody_accumulate(coeff * (-1.0j) * sinfactor, self, daga, undaga,
+                                              dagb, undagb)
+        return out
+
+    # ---- orbital rotation by column operators (fqe_data.py:1476-1535) ---------------------
+    def apply_columns_recursive_inplace(self, mat1, mat2) -> None:
+        """For icol = 0..norb-1: C <- (1 + sum_i mat1[i,icol] a+_{i,alpha} a_{icol,alpha}) C, then
+        the same with mat2 on the beta strings.  Only called from ``Wavefunction.transform``."""
+        _require_cuda()
+        norb = self.norb()
+        mat1, mat2 = _host_c128(mat1), _host_c128(mat2)
+        if mat1.shape != (norb, norb) or mat2.shape != (norb, norb):
+            raise ValueError("column operators must be norb x norb")
+        ptr = self._check_coeff(self.coeff).data_ptr()
+        _lib.call("fqeb_apply_columns", self._core.handle, 0, mat1.ctypes.data, ptr, _stream())
+        _lib.call("fqeb_apply_columns", self._core.handle, 1, mat2.ctypes.data, ptr, _stream())

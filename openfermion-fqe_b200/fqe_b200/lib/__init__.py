@@ -66,6 +66,13 @@ SIGNATURES = {
     "fqeb_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int64)]),
     "fqeb_dc_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fqeb_dc_evolve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fqeb_apply_columns": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "fqeb_apply_diagonal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fqeb_evolve_diagonal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fqeb_nbody_accumulate": (c_int, [c_void_p, c_double, c_double, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "fqeb_sparse_scale": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, c_double,
+                                  c_double, c_void_p, c_void_p]),
     "fqeb_reduce_scratch_bytes": (c_size_t, []),
     "fqeb_zaxpy": (c_int, [c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "fqeb_zscal": (c_int, [c_int64, c_double, c_double, c_void_p, c_void_p]),

@@ -19,10 +19,12 @@ from typing import Dict, KeysView, List, Optional, Tuple, Union
 
 import numpy
 import torch
+from scipy import linalg
 from scipy.special import factorial, jv
 
 from fqe_b200.fqe_data import DenseOperator, FqeData
-from fqe_b200.hamiltonians import diagonal_coulomb, hamiltonian, restricted_hamiltonian
+from fqe_b200.hamiltonians import (diagonal_coulomb, diagonal_hamiltonian, hamiltonian,
+                                   restricted_hamiltonian, sparse_hamiltonian)
 
 
 def alpha_beta_electrons(nele: int, m_s: int) -> Tuple[int, int]:
@@ -197,6 +199,10 @@ class Wavefunction:
         if not hamil.conserve_number():
             raise TypeError('Number non-conserving hamiltonian passed to'
                             ' number conserving wavefunction')
+        if isinstance(hamil, sparse_hamiltonian.SparseHamiltonian):
+            return self._apply_few_nbody(hamil)
+        if isinstance(hamil, diagonal_hamiltonian.Diagonal):
+            return self._apply_diagonal(hamil)
         if isinstance(hamil, diagonal_coulomb.DiagonalCoulomb):
             return self._apply_diagonal_coulomb(hamil)
         if isinstance(hamil, restricted_hamiltonian.RestrictedHamiltonian):
@@ -206,7 +212,7 @@ class Wavefunction:
             return self._apply_array(hamil.tensors(), hamil.e_0())
         raise NotImplementedError(
             f"{type(hamil).__name__} is outside the B200 hot path (RestrictedHamiltonian, "
-            "DiagonalCoulomb)")
+            "DiagonalCoulomb, Diagonal, SparseHamiltonian)")
 
     def _dense_operator(self, array: Tuple[numpy.ndarray, ...]) -> DenseOperator:
         if len(array) < 1 or len(array) > 4:
@@ -238,6 +244,15 @@ class Wavefunction:
             return out
         return self._apply_operator(self._dense_operator(array), e_0)
 
+    def _apply_diagonal(self, hamil: diagonal_hamiltonian.Diagonal) -> 'Wavefunction':
+        """(wavefunction.py:401-419)"""
+        out = copy.deepcopy(self)
+        for sec in out._civec.values():
+            sec.apply_diagonal_inplace(hamil.diag_values())
+        if numpy.abs(hamil.e_0()) > 1.e-15:
+            out.ax_plus_y(hamil.e_0(), self)
+        return out
+
     def _apply_diagonal_coulomb(self, hamil: diagonal_coulomb.DiagonalCoulomb) -> 'Wavefunction':
         out = copy.deepcopy(self)
         diag, array = hamil._tensor[1], hamil._tensor[2]
@@ -260,13 +275,29 @@ class Wavefunction:
         if not isinstance(expansion, int):
             raise TypeError("expansion must be an int. You provided {}".format(expansion))
         assert algo in ['taylor', 'chebyshev']
-        if not isinstance(hamil, restricted_hamiltonian.RestrictedHamiltonian):
+        sparse = isinstance(hamil, sparse_hamiltonian.SparseHamiltonian)
+        if not sparse and not isinstance(hamil, restricted_hamiltonian.RestrictedHamiltonian):
             raise NotImplementedError(
-                "apply_generated_unitary is accelerated for RestrictedHamiltonian only")
+                "apply_generated_unitary covers RestrictedHamiltonian and SparseHamiltonian")
         base = self
         self.last_expansion_order = 0
 
-        if algo == 'taylor':
+        if algo == 'taylor' and sparse:
+            # term-by-term application of the prepared operator (wavefunction.py:550-561)
+            ham_iht = hamil.iht(time)
+            time_evol = copy.deepcopy(base)
+            work = copy.deepcopy(base)
+            for order in range(1, expansion):
+                work = work.apply(ham_iht)
+                coeff = 1.0 / factorial(order)
+                wnorm = time_evol._axpy_norm(coeff, work)
+                if wnorm * numpy.abs(coeff) < accuracy:
+                    break
+            else:
+                raise RuntimeError("maximum taylor expansion limit reached")
+            self.last_expansion_order = order
+
+        elif algo == 'taylor':
             # -i*t*H is purely imaginary for real integrals: the operator is prepared
             # once (real-GEMM mode) and reused by every term.  The tuple re-wrap of the
             # reference drops e_0 inside the loop (fqe_decorators.py:68-73).
@@ -292,9 +323,11 @@ class Wavefunction:
             eshift = -(spec_lim[0] + ascale * wprime)
             tensors = hamil.tensors()
             e_0 = hamil.e_0()
-            op = self._dense_operator(tensors) if len(tensors) <= 2 else None
+            op = self._dense_operator(tensors) if not sparse and len(tensors) <= 2 else None
 
             def _h(x: 'Wavefunction') -> 'Wavefunction':
+                if sparse:
+                    return x.apply(hamil)
                 return x._apply_operator(op, e_0) if op is not None else x._apply_array(tensors, e_0)
 
             time_evol = copy.deepcopy(base)
@@ -329,24 +362,40 @@ class Wavefunction:
         if not hamil.conserve_number():
             raise TypeError('Number non-conserving hamiltonian passed to'
                             ' number conserving wavefunction')
-        is_diag = (hamil.quadratic() and hamil.diagonal()) or hamil.diagonal_coulomb()
-        if inplace and (not is_diag and not hamil.quadratic()):
-            raise ValueError("Inplace is not implemented for this case")
-        work_wfn = self if inplace else copy.deepcopy(self)
+        individual = isinstance(hamil, sparse_hamiltonian.SparseHamiltonian) and \
+            hamil.is_individual()
+        work_wfn = self
+        if not individual:
+            is_diag = (hamil.quadratic() and hamil.diagonal()) or hamil.diagonal_coulomb()
+            if inplace and (not is_diag and not hamil.quadratic()):
+                raise ValueError("Inplace is not implemented for this case")
+            work_wfn = self if inplace else copy.deepcopy(self)
 
-        if hamil.diagonal_coulomb():
+        if individual:
+            final_wfn = self._evolve_individual_nbody(time, hamil, inplace)
+        elif isinstance(hamil, sparse_hamiltonian.SparseHamiltonian):
+            final_wfn = work_wfn.apply_generated_unitary(time, 'taylor', hamil)
+        elif hamil.quadratic():
+            # (wavefunction.py:1013-1034) diagonal: one pass; otherwise rotate the orbitals to
+            # the eigenbasis of h1, evolve the diagonal, rotate back with the same L, U factors
+            if hamil.dim() != self._norb:
+                raise NotImplementedError("only spatial-orbital (restricted) tensors are supported")
+            if hamil.diagonal():
+                ihtdiag = -1.j * time * hamil.diag_values()
+                final_wfn = work_wfn._evolve_diagonal(ihtdiag, inplace)
+            else:
+                transformation = hamil.calc_diag_transform()
+                permu, low, upp, work_wfn = work_wfn.transform(transformation)
+                ci_trans = transformation @ permu
+                h1e = hamil.transform(ci_trans)
+                ihtdiag = -1.j * time * h1e.diagonal()
+                evolved_wfn = work_wfn._evolve_diagonal(ihtdiag, inplace=True)
+                _, _, _, final_wfn = evolved_wfn.transform(ci_trans.T.conj(), low, upp)
+        elif hamil.diagonal_coulomb():
             diag, vij = hamil.iht(time)
             final_wfn = work_wfn._evolve_diagonal_coulomb_inplace(diag, vij)
         elif isinstance(hamil, restricted_hamiltonian.RestrictedHamiltonian):
-            # Quadratic Hamiltonians go through an orbital rotation in the reference
-            # (wavefunction.py:1013-1034); here they take the same Taylor route as the
-            # general case, which agrees to the series accuracy (1e-15).
-            if hamil.quadratic():
-                # that branch of the reference applies the e_0 phase once, not twice
-                bare = restricted_hamiltonian.RestrictedHamiltonian(hamil.tensors(), e_0=0.0)
-                final_wfn = work_wfn.apply_generated_unitary(time, 'taylor', bare)
-            else:
-                final_wfn = work_wfn.apply_generated_unitary(time, 'taylor', hamil)
+            final_wfn = work_wfn.apply_generated_unitary(time, 'taylor', hamil)
         else:
             raise NotImplementedError(
                 f"time_evolve with {type(hamil).__name__} is outside the B200 hot path")
@@ -355,6 +404,154 @@ class Wavefunction:
             final_wfn.scale(numpy.exp(-1.j * time * hamil.e_0()))
         self.last_expansion_order = getattr(work_wfn, "last_expansion_order", 0)
         return final_wfn
+
+    # ---- individual n-body operators (wavefunction.py:1135-1328) ---------------------------
+    def _operator_lists(self, alpha, beta):
+        for oper in list(alpha) + list(beta):
+            assert oper[0] < self._norb
+        daga, undaga, dagb, undagb = sparse_hamiltonian.SparseHamiltonian.split(alpha, beta)
+        if len(daga) + len(dagb) != len(undaga) + len(undagb):
+            raise ValueError('Number non-conserving operators specified')
+        if len(daga) != len(undaga) or len(dagb) != len(undagb):
+            raise NotImplementedError("spin-changing individual operators need number-sector "
+                                      "wavefunctions, which are outside the B200 hot path")
+        return daga, undaga, dagb, undagb
+
+    def _apply_individual_nbody(self, hamil: sparse_hamiltonian.SparseHamiltonian,
+                                base: Optional['Wavefunction'] = None) -> 'Wavefunction':
+        assert isinstance(hamil, sparse_hamiltonian.SparseHamiltonian)
+        if hamil.nterms() > 1:
+            raise ValueError('Indivisual n-body code is called with multiple terms')
+        [(coeff, alpha, beta)] = hamil.terms()
+        daga, undaga, dagb, undagb = self._operator_lists(alpha, beta)
+        out = self.empty_copy() if base is None else base
+        for key in self._civec.keys():
+            out._civec[key].apply_individual_nbody_accumulate(coeff, self._civec[key], daga,
+                                                              undaga, dagb, undagb)
+        return out
+
+    def _apply_few_nbody(self, hamil: sparse_hamiltonian.SparseHamiltonian) -> 'Wavefunction':
+        out = None
+        for oper in hamil.terms_hamiltonian():
+            out = self._apply_individual_nbody(oper, base=out)
+        if out is None:
+            out = copy.deepcopy(self)
+        if numpy.abs(hamil.e_0()) > 1.e-15:
+            out.ax_plus_y(hamil.e_0(), self)
+        return out
+
+    def _evolve_individual_nbody(self, time: float, hamil: sparse_hamiltonian.SparseHamiltonian,
+                                 inplace: bool = False) -> 'Wavefunction':
+        """exp(-i t (T + T^+)) for one normal-ordered operator T given with (or as) its
+        Hermitian conjugate (wavefunction.py:1192-1302)."""
+        if not isinstance(hamil, sparse_hamiltonian.SparseHamiltonian):
+            raise TypeError('Expected a Hamiltonian Object but received {}'.format(hamil))
+        if hamil.nterms() > 2:
+            raise ValueError('Individual n-body code is called with multiple terms')
+        if hamil.nterms() == 2:
+            [(coeff0, alpha0, beta0), (coeff1, alpha1, beta1)] = hamil.terms()
+            check = all((a[0], a[1] ^ 1) in alpha1 for a in alpha0) and \
+                all((b[0], b[1] ^ 1) in beta1 for b in beta0)
+        else:
+            [(coeff0, alpha0, beta0)] = hamil.terms()
+            check = all((a[0], a[1] ^ 1) in alpha0 for a in alpha0) and \
+                all((b[0], b[1] ^ 1) in beta0 for b in beta0)
+        if not check:
+            raise ValueError('Operators in _evolve_individual_nbody is not Hermitian')
+        if hamil.nterms() == 1:
+            coeff0 = coeff0 * 0.5
+        daga, undaga, dagb, undagb = self._operator_lists(alpha0, beta0)
+        if hamil.nterms() == 2:
+            parity = (-1)**(len(alpha0) * len(beta0) + len(daga) * (len(daga) - 1) // 2 +
+                            len(dagb) * (len(dagb) - 1) // 2 +
+                            len(undaga) * (len(undaga) - 1) // 2 +
+                            len(undagb) * (len(undagb) - 1) // 2)
+            if not numpy.abs(coeff0 - numpy.conj(coeff1) * parity) < 1.0e-8:
+                raise ValueError('Coefficients in _evolve_individual_nbody is not Hermitian')
+        if daga == undaga and dagb == undagb:
+            out = self if inplace else copy.deepcopy(self)
+            for sector in out._civec.values():
+                sector.evolve_inplace_individual_nbody_trivial(time, coeff0, daga, dagb)
+        else:
+            out = self.empty_copy(zero=False)
+            for label, isec in self._civec.items():
+                out._civec[label] = isec.evolve_individual_nbody_nontrivial(
+                    time, coeff0, daga, undaga, dagb, undagb)
+        return out
+
+    def _evolve_diagonal(self, ithdiag: numpy.ndarray, inplace: bool = False) -> 'Wavefunction':
+        """(wavefunction.py:1056-1077)"""
+        wfn = self if inplace else copy.deepcopy(self)
+        for sec in wfn._civec.values():
+            sec.evolve_diagonal(ithdiag, inplace=True)
+        return wfn
+
+    def transform(self, rotation: numpy.ndarray, low: Optional[numpy.ndarray] = None,
+                  upp: Optional[numpy.ndarray] = None):
+        """Rotate the orbitals by the unitary ``rotation`` (norb x norb, the same for both
+        spins, or a block-diagonal 2norb x 2norb).  Returns (permutation, L, U, self); the
+        wavefunction is transformed IN PLACE like the reference's (wavefunction.py:813-959).
+
+        rotation^H = P L U; the transformation operator factorises into 2*norb column
+        operators, each applied by one pass of ``fqeb_apply_columns``."""
+        norb = self._norb
+        external = low is not None
+        assert external == (upp is not None)
+        if external:
+            assert numpy.allclose(rotation, low @ upp)
+
+        def ludecomp(rotmat):
+            return linalg.lu(rotmat.transpose().conjugate())
+
+        def transpose_matrix(low, upp):
+            # Hermitian conjugate of the factors with the diagonal moved into the upper one
+            ndim = low.shape[0]
+            lowt, uppt = low.astype(numpy.complex128), upp.astype(numpy.complex128)
+            for irow in range(ndim):
+                uppt[irow, irow + 1:] /= uppt[irow, irow]
+                lowt[irow, irow], uppt[irow, irow] = uppt[irow, irow], lowt[irow, irow]
+                for icol in range(irow):
+                    lowt[irow, icol] *= lowt[icol, icol]
+            return uppt.T.conj(), lowt.T.conj()
+
+        def process_matrix(low, upp):
+            ndim = low.shape[0]
+            output = linalg.solve_triangular(upp, numpy.identity(ndim))
+            return output - numpy.tril(low, -1) - numpy.identity(ndim)
+
+        def factors(rot, low, upp):
+            if low is None:
+                perm, low, upp = ludecomp(rot)
+                lowt, uppt = transpose_matrix(low, upp)
+                return perm, low, upp, process_matrix(lowt, uppt)
+            return None, low, upp, process_matrix(low, upp)
+
+        if rotation.shape[0] == norb:
+            perm, low, upp, output = factors(rotation, low, upp)
+            for sec in self._civec.values():
+                sec.apply_columns_recursive_inplace(output, output)
+        elif rotation.shape[0] == 2 * norb:
+            assert numpy.std(rotation[:norb, norb:]) + numpy.std(rotation[norb:, :norb]) < 1.0e-8
+            la = None if low is None else low[:norb, :norb]
+            ua = None if upp is None else upp[:norb, :norb]
+            lb = None if low is None else low[norb:, norb:]
+            ub = None if upp is None else upp[norb:, norb:]
+            perm1, low1, upp1, output1 = factors(rotation[:norb, :norb], la, ua)
+            perm2, low2, upp2, output2 = factors(rotation[norb:, norb:], lb, ub)
+            for sec in self._civec.values():
+                sec.apply_columns_recursive_inplace(output1, output2)
+            if not external:
+                perm, low, upp = (numpy.zeros_like(rotation), numpy.zeros_like(rotation),
+                                  numpy.zeros_like(rotation))
+                for full, blk1, blk2 in ((perm, perm1, perm2), (low, low1, low2),
+                                         (upp, upp1, upp2)):
+                    full[:norb, :norb] = blk1
+                    full[norb:, norb:] = blk2
+            else:
+                perm = None
+        else:
+            raise ValueError("rotation must be norb x norb or 2norb x 2norb")
+        return perm, low, upp, self
 
     def _evolve_diagonal_coulomb_inplace(self, diag: numpy.ndarray,
                                          vij: numpy.ndarray) -> 'Wavefunction':

@@ -450,6 +450,259 @@ def time_evolve_dc(g, coeff, time, diag, vij, e0=0.0):
 # --------------------------------------------------------------------------
 # independent check: dense matrix of H in the determinant basis
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# 8f rank 1: orbital rotation by LU column operators, quadratic evolution
+# (wavefunction.py:813-959, 1013-1034; fqe_data.py:1476-1535; lib/fqe_data.c:305-347)
+# --------------------------------------------------------------------------
+def apply_column(g: OracleGraph, coeff: np.ndarray, col: np.ndarray, icol: int,
+                 spin: int) -> np.ndarray:
+    """(1 + sum_i col[i] a^+_i a_icol) acting on one spin, out of place.  The reference does
+    it in place: targets (icol empty) accumulate from sources (icol occupied), which are then
+    scaled by 1 + col[icol] (fqe_data.py:1494-1504, lib/fqe_data.c:318-346)."""
+    out = coeff.copy()
+    maps = g.alpha_map if spin == 0 else g.beta_map
+    for i in range(g.norb):
+        m = maps[(i, icol)]
+        if m.shape[0] == 0:
+            continue
+        if spin == 0:
+            np.add.at(out, (m[:, 1], slice(None)), col[i] * coeff[m[:, 0], :] * m[:, 2][:, None])
+        else:
+            np.add.at(out, (slice(None), m[:, 1]), col[i] * coeff[:, m[:, 0]] * m[:, 2][None, :])
+    return out
+
+
+def apply_columns_recursive(g: OracleGraph, coeff: np.ndarray, mat1: np.ndarray,
+                            mat2: np.ndarray) -> np.ndarray:
+    """FqeData.apply_columns_recursive_inplace (fqe_data.py:1506-1535): all alpha columns in
+    ascending order, then all beta columns."""
+    c = np.asarray(coeff, dtype=np.complex128)
+    for icol in range(g.norb):
+        c = apply_column(g, c, mat1[:, icol], icol, 0)
+    for icol in range(g.norb):
+        c = apply_column(g, c, mat2[:, icol], icol, 1)
+    return c
+
+
+def lu_factors(rotation: np.ndarray):
+    """ludecomp + transpose_matrix of Wavefunction.transform (wavefunction.py:838-887):
+    P, L, U of rotation^H and their conjugate-transposed, diagonal-swapped counterparts."""
+    from scipy import linalg
+    perm, low, upp = linalg.lu(np.asarray(rotation).T.conj())
+    lowt, uppt = low.copy(), upp.copy()
+    n = low.shape[0]
+    for irow in range(n):
+        uppt[irow, irow + 1:] /= uppt[irow, irow]
+        lowt[irow, irow], uppt[irow, irow] = uppt[irow, irow], lowt[irow, irow]
+        for icol in range(irow):
+            lowt[irow, icol] *= lowt[icol, icol]
+    return perm, low, upp, uppt.T.conj(), lowt.T.conj()
+
+
+def column_operator(low: np.ndarray, upp: np.ndarray) -> np.ndarray:
+    """process_matrix (wavefunction.py:889-909): inv(upp) - strict_lower(low) - 1."""
+    from scipy import linalg
+    n = low.shape[0]
+    out = linalg.solve_triangular(upp, np.identity(n))
+    out = out - np.tril(low, -1) - np.identity(n)
+    return out
+
+
+def transform(g: OracleGraph, coeff: np.ndarray, rotation: np.ndarray, low=None, upp=None):
+    """Wavefunction.transform for one number- and spin-conserving sector with a spatial
+    rotation (wavefunction.py:918-928).  Returns (perm, low, upp, coeff')."""
+    perm = None
+    if low is None:
+        perm, low, upp, lowt, uppt = lu_factors(rotation)
+    else:
+        lowt, uppt = low, upp
+    mat = column_operator(lowt, uppt)
+    return perm, low, upp, apply_columns_recursive(g, coeff, mat, mat)
+
+
+def evolve_diagonal(g: OracleGraph, coeff: np.ndarray, array: np.ndarray) -> np.ndarray:
+    """FqeData.evolve_diagonal (fqe_data.py:203-261): C[a,b] *= exp(sum_{i in a} array[i]) *
+    exp(sum_{i in b} array[i])."""
+    ea = np.exp(occupations(g.astr, g.norb) @ np.asarray(array, dtype=np.complex128))
+    eb = np.exp(occupations(g.bstr, g.norb) @ np.asarray(array, dtype=np.complex128))
+    return coeff * ea[:, None] * eb[None, :]
+
+
+def apply_diagonal(g: OracleGraph, coeff: np.ndarray, array: np.ndarray) -> np.ndarray:
+    """FqeData.apply_diagonal_inplace (fqe_data.py:170-201)."""
+    da = occupations(g.astr, g.norb) @ np.asarray(array, dtype=np.complex128)
+    db = occupations(g.bstr, g.norb) @ np.asarray(array, dtype=np.complex128)
+    return coeff * (da[:, None] + db[None, :])
+
+
+def time_evolve_quadratic(g: OracleGraph, coeff: np.ndarray, time: float, h1: np.ndarray,
+                          e0=0.0) -> np.ndarray:
+    """Quadratic branch of Wavefunction.time_evolve (wavefunction.py:1013-1034): rotate to the
+    eigenbasis of h1, evolve the diagonal, rotate back with the same L, U factors."""
+    h1 = np.asarray(h1, dtype=np.complex128)
+    _, trans = np.linalg.eigh(h1)
+    perm, low, upp, c = transform(g, coeff, trans)
+    ci_trans = trans @ perm
+    h1d = ci_trans.conj().T @ h1 @ ci_trans
+    c = evolve_diagonal(g, c, -1.0j * time * h1d.diagonal())
+    _, _, _, c = transform(g, c, ci_trans.T.conj(), low, upp)
+    if abs(e0) > 1.0e-15:
+        c = c * np.exp(-1.0j * time * e0)
+    return c
+
+
+# --------------------------------------------------------------------------
+# 8f rank 2: individual n-body operators
+# (fci_graph.py:511-570; fqe_data.py:1558-1653, 2385-2580; wavefunction.py:1135-1328)
+# --------------------------------------------------------------------------
+def make_mapping_each(strings: np.ndarray, norb: int, nele: int, dag, undag):
+    """(source index, target index, sign) of prod a^+_dag prod a_undag on one spin; the
+    rightmost operator acts first, sign = (-1)^(occupied orbitals above the one acted on)
+    (fci_graph.py:546-569, lib/fci_graph.c:223-264)."""
+    src, tgt, sgn = [], [], []
+    for idx, s in enumerate(int(x) for x in strings):
+        cur, parity, ok = s, 0, True
+        for o in reversed(list(undag)):
+            if not (cur >> o) & 1:
+                ok = False
+                break
+            parity += bin(cur >> (o + 1)).count("1")
+            cur &= ~(1 << o)
+        if not ok:
+            continue
+        for o in reversed(list(dag)):
+            if (cur >> o) & 1:
+                ok = False
+                break
+            parity += bin(cur >> (o + 1)).count("1")
+            cur |= 1 << o
+        if not ok:
+            continue
+        src.append(idx)
+        tgt.append(cur)
+        sgn.append(1 - 2 * (parity & 1))
+    tgt_idx = string_addresses(np.array(tgt, dtype=np.uint64), norb, nele) if tgt else []
+    return (np.array(src, dtype=np.int64), np.array(tgt_idx, dtype=np.int64),
+            np.array(sgn, dtype=np.int64))
+
+
+def apply_individual_nbody(g: OracleGraph, coeff_in: np.ndarray, coeff: complex, daga, undaga,
+                           dagb, undagb, out: np.ndarray = None) -> np.ndarray:
+    """out[ta, tb] += coeff * pa * pb * in[sa, sb]  (fqe_data.py:1590-1667)."""
+    if out is None:
+        out = np.zeros_like(coeff_in, dtype=np.complex128)
+    sa, ta, pa = make_mapping_each(g.astr, g.norb, g.nalpha, daga, undaga)
+    sb, tb, pb = make_mapping_each(g.bstr, g.norb, g.nbeta, dagb, undagb)
+    if sa.size and sb.size:
+        out[np.ix_(ta, tb)] += coeff * (pa[:, None] * pb[None, :]) * coeff_in[np.ix_(sa, sb)]
+    return out
+
+
+def _occupied_mask(strings, occ, emp):
+    pm = sum(1 << int(o) for o in set(occ))
+    hm = sum(1 << int(o) for o in set(emp))
+    return np.array([(int(s) & pm) == pm and (int(s) & hm) == 0 for s in strings], dtype=bool)
+
+
+def sparse_scale(g: OracleGraph, coeff: np.ndarray, factor: complex, opa, oha, opb, ohb):
+    """apply_cos_inplace / trivial evolution kernel: scale the determinants with opa, opb
+    occupied and oha, ohb empty (fqe_data.py:2515-2580)."""
+    ma, mb = _occupied_mask(g.astr, opa, oha), _occupied_mask(g.bstr, opb, ohb)
+    out = coeff.copy()
+    out[np.ix_(ma, mb)] *= factor
+    return out
+
+
+def evolve_individual_trivial(g, coeff, time, zc, opa, opb):
+    """fqe_data.py:2385-2433"""
+    n_a, n_b = len(opa), len(opb)
+    zc = zc * (-1)**(n_a * (n_a - 1) // 2 + n_b * (n_b - 1) // 2)
+    return sparse_scale(g, coeff, np.exp(-time * np.real(zc) * 2.j), opa, [], opb, [])
+
+
+def evolve_individual_nontrivial(g, coeff, time, zc, daga, undaga, dagb, undagb):
+    """exp(-i t (T + T^+)) with T^2 = 0 (fqe_data.py:2435-2513)."""
+    def isolate(dag, undag, dagwork, undagwork, number):
+        par = 0
+        for cur in dag:
+            if cur in undag:
+                i1, i2 = dagwork.index(cur), undagwork.index(cur)
+                par += len(dagwork) - (i1 + 1) + i2
+                dagwork.remove(cur)
+                undagwork.remove(cur)
+                number.append(cur)
+        return par
+
+    dwa, uwa, dwb, uwb = list(daga), list(undaga), list(dagb), list(undagb)
+    numa, numb = [], []
+    parity = isolate(daga, undaga, dwa, uwa, numa) + isolate(dagb, undagb, dwb, uwb, numb)
+    ncoeff = zc * (-1)**parity
+    absol = abs(ncoeff)
+    sinf = np.sin(time * absol) / absol
+    out = sparse_scale(g, coeff, np.cos(time * absol), numa + dwa, uwa, numb + dwb, uwb)
+    out = sparse_scale(g, out, np.cos(time * absol), numa + uwa, dwa, numb + uwb, dwb)
+    phase = (-1)**((len(daga) + len(undaga)) * (len(dagb) + len(undagb)))
+    apply_individual_nbody(g, coeff, np.conj(zc) * phase * (-1.0j) * sinf, undaga, daga, undagb,
+                           dagb, out=out)
+    apply_individual_nbody(g, coeff, zc * (-1.0j) * sinf, daga, undaga, dagb, undagb, out=out)
+    return out
+
+
+def split_operator(alpha, beta):
+    daga = [o[0] for o in alpha if o[1] == 1]
+    undaga = [o[0] for o in alpha if o[1] == 0]
+    dagb = [o[0] for o in beta if o[1] == 1]
+    undagb = [o[0] for o in beta if o[1] == 0]
+    return daga, undaga, dagb, undagb
+
+
+def sparse_apply(g, coeff, operators, e0=0.0):
+    """Wavefunction._apply_few_nbody (wavefunction.py:1304-1328) for operators given in the
+    SparseHamiltonian internal form (coeff, alpha ops, beta ops)."""
+    out = np.zeros_like(coeff, dtype=np.complex128) if operators else coeff.copy()
+    for zc, alpha, beta in operators:
+        apply_individual_nbody(g, coeff, zc, *split_operator(alpha, beta), out=out)
+    if abs(e0) > 1.0e-15:
+        out = out + e0 * coeff
+    return out
+
+
+def ladder_sequence_apply(g: OracleGraph, coeff: np.ndarray, ops, zc: complex = 1.0):
+    """INDEPENDENT brute force: apply zc * (product of spin-orbital ladder operators, in the
+    order written, rightmost first) to the state.  ops = ((spin_orbital, 1|0), ...) with spin
+    orbital 2k = (k, alpha), 2k+1 = (k, beta).  A determinant is
+    [alpha creators, highest orbital leftmost][beta creators, highest leftmost]|0>, the
+    convention behind make_mapping_each's count-bits-above parity and the alpha-then-beta
+    string product (fci_graph.py:100-106).  Returns the projection back onto the sector."""
+    state = {}
+    for ia, sa in enumerate(int(x) for x in g.astr):
+        for ib, sb in enumerate(int(x) for x in g.bstr):
+            if coeff[ia, ib] != 0:
+                state[(sa, sb)] = complex(coeff[ia, ib])
+    for so, dagger in reversed(list(ops)):
+        orb, beta = so // 2, so % 2
+        new = {}
+        for (sa, sb), amp in state.items():
+            cur = sb if beta else sa
+            occupied = (cur >> orb) & 1
+            if occupied == dagger:
+                continue
+            par = bin(cur >> (orb + 1)).count("1")
+            if beta:
+                par += bin(sa).count("1")
+            cur ^= 1 << orb
+            key = (sa, cur) if beta else (cur, sb)
+            new[key] = new.get(key, 0.0) + amp * (1 - 2 * (par & 1))
+        state = new
+    out = np.zeros((g.lena, g.lenb), dtype=np.complex128)
+    aidx = {int(s): i for i, s in enumerate(g.astr)}
+    bidx = {int(s): i for i, s in enumerate(g.bstr)}
+    for (sa, sb), amp in state.items():
+        if sa in aidx and sb in bidx:
+            out[aidx[sa], bidx[sb]] += zc * amp
+    return out
+
+
 def dense_hamiltonian(g, h1, h2, e0=0.0):
     """Column-by-column H matrix, as tests/evolution_test.py:527-594 builds it."""
     dim = g.lena * g.lenb

@@ -21,6 +21,11 @@ Outputs (all small, committed):
                                 from profiling/Hring_12.hdf5 with tests/golden/hdf5_mini.py,
                                 energies, and signatures (norms, 512 sampled coefficients, 8
                                 random projections) of H|HF> and of the state evolved to t=0.1
+    ref_transform.npz           SURVEY 8f rank 1: Wavefunction.transform (LU column rotations),
+                                quadratic time_evolve, Diagonal apply / evolve, evolve_diagonal
+                                (`--only transform` regenerates just this file)
+    ref_nbody.npz               SURVEY 8f rank 2: individual n-body apply / exact evolution through
+                                FqeData and through Wavefunction + SparseHamiltonian (`--only nbody`)
 """
 import os
 import shutil
@@ -117,6 +122,111 @@ def rand_state(shape, rng):
     return c / np.linalg.norm(c)
 
 
+def transform_goldens(fqe):
+    """Orbital rotations and quadratic evolution through the reference's public API."""
+    import copy
+    from scipy.linalg import expm
+    out = {}
+    cases = [("ta", 4, 0, 4, False), ("tb", 5, 1, 6, False), ("tc", 3, -1, 5, True),
+             ("td", 6, 0, 6, False), ("te", 2, 2, 5, False), ("tf", 8, 0, 8, False)]
+    for tag, n, sz, norb, real in cases:
+        rng = np.random.default_rng(20260600 + 100 * norb + ord(tag[1]))
+        a = rng.standard_normal((norb, norb))
+        b = np.zeros((norb, norb)) if real else rng.standard_normal((norb, norb))
+        if real:   # real orthogonal rotation
+            rot = expm(0.4 * (a - a.T))
+        else:
+            k = 0.5 * ((a + 1j * b) + (a + 1j * b).conj().T)
+            rot = expm(-0.7j * k)
+        h1 = 0.5 * ((a + 1j * b) + (a + 1j * b).conj().T)
+        if real:
+            h1 = h1.real.astype(np.complex128)
+        diag = rng.standard_normal(norb)
+        wfn = fqe.Wavefunction([[n, sz, norb]])
+        shape = wfn.get_coeff((n, sz)).shape
+        c0 = rand_state(shape, rng)
+        wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0.copy()})
+        t, e0 = 0.37, -0.4
+        out[f"{tag}_meta"] = np.array([n, sz, norb], dtype=np.int64)
+        out[f"{tag}_c0"], out[f"{tag}_rot"], out[f"{tag}_h1"], out[f"{tag}_diag"] = c0, rot, h1, diag
+        out[f"{tag}_t"], out[f"{tag}_e0"] = np.array([t]), np.array([e0])
+        perm, low, upp, res = copy.deepcopy(wfn).transform(rot)
+        out[f"{tag}_perm"], out[f"{tag}_low"], out[f"{tag}_upp"] = perm, low, upp
+        out[f"{tag}_transformed"] = res.get_coeff((n, sz))
+        ham = fqe.get_restricted_hamiltonian((h1,), e_0=e0)
+        out[f"{tag}_quad_evolve"] = wfn.time_evolve(t, ham).get_coeff((n, sz))
+        out[f"{tag}_quad_apply"] = wfn.apply(ham).get_coeff((n, sz))
+        dham = fqe.get_diagonal_hamiltonian(diag.astype(np.complex128), e_0=e0)
+        out[f"{tag}_diag_apply"] = wfn.apply(dham).get_coeff((n, sz))
+        out[f"{tag}_diag_evolve"] = wfn.time_evolve(t, dham).get_coeff((n, sz))
+        arr = (-1j * t * diag).astype(np.complex128)
+        out[f"{tag}_evolve_diagonal"] = wfn.sector((n, sz)).evolve_diagonal(arr)
+        # exact answer for the quadratic evolution from the dense one-particle picture:
+        # <x| exp(-itH) |psi> checked through U = exp(-i t h1) as an orbital rotation
+        out[f"{tag}_quad_unitary"] = expm(-1j * t * h1)
+    np.savez_compressed(os.path.join(HERE, "ref_transform.npz"), **out)
+    print("ref_transform.npz", os.path.getsize(os.path.join(HERE, "ref_transform.npz")), "bytes")
+
+
+def nbody_goldens(fqe):
+    """Individual n-body operators through FqeData and, with the internal
+    operator lists set by hand (openfermion's FermionOperator is not available here),
+    through Wavefunction.apply / time_evolve with a SparseHamiltonian."""
+    from fqe.hamiltonians.sparse_hamiltonian import SparseHamiltonian
+    from fqe.hamiltonians.hamiltonian import Hamiltonian
+
+    def sparse(operators, e_0=0.0):
+        sh = SparseHamiltonian.__new__(SparseHamiltonian)
+        Hamiltonian.__init__(sh, e_0=e_0)
+        sh._operators = [(c, list(a), list(b)) for c, a, b in operators]
+        sh._conserve_spin = True
+        sh._rank = max(len(a) + len(b) for _, a, b in operators)
+        return sh
+
+    ops = [([1], [0], [], []), ([], [], [2], [1]), ([2], [0], [1], [3]),
+           ([3, 1], [2, 0], [], []), ([1], [1], [2], [0]), ([2, 0], [2, 1], [1], [1]),
+           ([0], [0], [1], [1]), ([2, 1], [1, 0], [3], [2]), ([3], [3], [], [])]
+    out = {"ops": np.array([repr(o) for o in ops])}
+    coeff, time = 0.3 - 0.2j, 0.41
+    out["coeff"], out["time"] = np.array([coeff]), np.array([time])
+    for tag, n, sz, norb in [("na", 4, 0, 4), ("nb", 5, 1, 6), ("nc", 6, 0, 6), ("nd", 3, -1, 5)]:
+        rng = np.random.default_rng(20260700 + 100 * norb + ord(tag[1]))
+        wfn = fqe.Wavefunction([[n, sz, norb]])
+        shape = wfn.get_coeff((n, sz)).shape
+        c0 = rand_state(shape, rng)
+        wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0.copy()})
+        out[f"{tag}_meta"], out[f"{tag}_c0"] = np.array([n, sz, norb], dtype=np.int64), c0
+        sec = wfn.sector((n, sz))
+        for k, (da, ua, db, ub) in enumerate(ops):
+            if max(da + ua + db + ub) >= norb:
+                continue
+            out[f"{tag}_apply{k}"] = sec.apply_individual_nbody(coeff, da, ua, db, ub).coeff
+            if da == ua and db == ub:
+                tmp = fqe.Wavefunction([[n, sz, norb]])
+                tmp.set_wfn(strategy="from_data", raw_data={(n, sz): c0.copy()})
+                tmp.sector((n, sz)).evolve_inplace_individual_nbody_trivial(time, coeff, da, db)
+                out[f"{tag}_trivial{k}"] = tmp.get_coeff((n, sz))
+            else:
+                out[f"{tag}_evolve{k}"] = sec.evolve_individual_nbody_nontrivial(
+                    time, coeff, da, ua, db, ub).coeff
+        # Wavefunction level: T + T^+ for T = c a+_2a a_0a a+_1b a_3b, one number operator,
+        # and a three-operator Hermitian sum that goes through the Taylor series
+        t_op = (coeff, [(2, 1), (0, 0)], [(1, 1), (3, 0)])
+        t_dag = (np.conj(coeff), [(0, 1), (2, 0)], [(3, 1), (1, 0)])
+        if norb > 3:
+            pair = sparse([t_op, t_dag], e_0=0.25)
+            out[f"{tag}_w_pair_apply"] = wfn.apply(pair).get_coeff((n, sz))
+            out[f"{tag}_w_pair_evolve"] = wfn.time_evolve(time, pair).get_coeff((n, sz))
+            num = sparse([(0.7, [(1, 1), (1, 0)], [(0, 1), (0, 0)])], e_0=-0.5)
+            out[f"{tag}_w_num_apply"] = wfn.apply(num).get_coeff((n, sz))
+            out[f"{tag}_w_num_evolve"] = wfn.time_evolve(time, num).get_coeff((n, sz))
+            three = sparse([t_op, t_dag, (0.4, [(1, 1), (1, 0)], [])], e_0=0.05)
+            out[f"{tag}_w_three_apply"] = wfn.apply(three).get_coeff((n, sz))
+            out[f"{tag}_w_three_evolve"] = wfn.time_evolve(0.05, three).get_coeff((n, sz))
+    np.savez_compressed(os.path.join(HERE, "ref_nbody.npz"), **out)
+    print("ref_nbody.npz", os.path.getsize(os.path.join(HERE, "ref_nbody.npz")), "bytes")
+
+
 def main():
     src = build_reference()
     install_stubs()
@@ -127,6 +237,10 @@ def main():
     from fqe.fqe_data import FqeData
 
     fqe.settings.use_accelerated_code = True
+    if "--only" in sys.argv:
+        {"transform": transform_goldens, "nbody": nbody_goldens}[
+            sys.argv[sys.argv.index("--only") + 1]](fqe)
+        return
 
     # ---- (2) the reference's shipped goldens for this path ------------------
     d = os.path.join(REF, "tests", "unittest_data", "fqe_data")
@@ -279,6 +393,8 @@ def main():
     print("H12 ring: E_init", e_init, "E_final", e_final, "E_HF(file)", float(mol.read("hf_energy")))
     for f in ("ref_unittest_fqe_data.npz", "ref_graphs.npz", "ref_api.npz", "ref_hring12.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+    transform_goldens(fqe)
+    nbody_goldens(fqe)
 
 
 if __name__ == "__main__":

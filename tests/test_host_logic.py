@@ -107,3 +107,67 @@ def test_synthetic_integrals_symmetry_classes():
     assert np.allclose(hm, hm.conj().T) and np.abs(hm.imag).max() > 1e-3
     c = synth.state(6, 4, seed=1)
     assert abs(np.linalg.norm(c) - 1) < 1e-14 and np.array_equal(c, synth.state(6, 4, seed=1))
+
+
+def test_diagonal_hamiltonian_container():
+    """Diagonal mirrors hamiltonians/diagonal_hamiltonian.py:26-121"""
+    import fqe_b200
+    from fqe_b200.hamiltonians.diagonal_hamiltonian import Diagonal
+    d = np.array([0.5, -1.0, 2.0], dtype=np.complex128)
+    h = fqe_b200.get_diagonal_hamiltonian(d, e_0=0.25)
+    assert isinstance(h, Diagonal)
+    assert h.dim() == 3 and h.rank() == 2 and h.quadratic() and h.diagonal()
+    assert not h.diagonal_coulomb() and h.conserve_number() and h.e_0() == 0.25
+    assert np.array_equal(h.diag_values(), d)
+    it = h.iht(0.1)
+    assert np.allclose(it.diag_values(), -0.1j * d) and np.array_equal(h.diag_values(), d)
+    assert h == Diagonal(d.copy(), e_0=0.25) and not (h == Diagonal(d + 1, e_0=0.25))
+    with pytest.raises(ValueError):
+        Diagonal(np.zeros((2, 2)))
+
+
+def test_quadratic_transform_helpers():
+    """RestrictedHamiltonian.calc_diag_transform / transform diagonalise h1
+    (restricted_hamiltonian.py:136-155)"""
+    import fqe_b200
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))
+    h1 = a + a.conj().T
+    ham = fqe_b200.get_restricted_hamiltonian((h1,))
+    assert ham.quadratic() and not ham.diagonal()
+    u = ham.calc_diag_transform()
+    hd = ham.transform(u)
+    assert np.allclose(hd, np.diag(np.diag(hd)), atol=1e-12)
+    assert np.allclose(np.sort(np.diag(hd).real), np.linalg.eigvalsh(h1))
+
+
+def test_sparse_hamiltonian_normal_ordering_against_brute_force():
+    """SparseHamiltonian's own normal ordering + alpha/beta split (openfermion is not available
+    here): the operator it encodes must act like the ladder-operator product as written"""
+    from fqe_b200.hamiltonians.sparse_hamiltonian import SparseHamiltonian, normal_ordered
+    assert normal_ordered({((1, 0), (2, 1)): 1.0}) == {((2, 1), (1, 0)): -1.0}
+    assert normal_ordered({((1, 0), (1, 1)): 1.0}) == {(): 1.0, ((1, 1), (1, 0)): -1.0}
+    assert normal_ordered({((3, 1), (3, 1)): 1.0}) == {}
+    g = O.graph(3, 2, 5)
+    rng = np.random.default_rng(9)
+    c = rng.standard_normal((g.lena, g.lenb)) + 1j * rng.standard_normal((g.lena, g.lenb))
+    cases = ["3^ 0 2^ 1", "0^ 2", "5 1^ 1 5^", "4^ 2^ 0 6", "1^ 3^ 7 5", "2 2^",
+             "6^ 1^ 3^ 3 7 0", "9^ 8 8^ 9", "0 4^ 3^ 7"]
+    for text in cases:
+        ham = SparseHamiltonian(text)
+        seq = tuple((int(t.rstrip('^')), 1 if t.endswith('^') else 0) for t in text.split())
+        ref = O.ladder_sequence_apply(g, c, seq)
+        ops = ham.terms()
+        spin_ok = all(sum(1 for o in a if o[1]) * 2 == len(a) and
+                      sum(1 for o in b if o[1]) * 2 == len(b) for _, a, b in ops)
+        if not spin_ok:
+            continue   # spin-changing products leave the sector; only the constructor is checked
+        out = O.sparse_apply(g, c, ops, ham.e_0())
+        assert np.abs(out - ref).max() < 1e-13, text
+    # a multi-term mapping with a constant: e_0 picks it up
+    ham = SparseHamiltonian({((0, 1), (2, 0)): 0.5, ((2, 1), (0, 0)): 0.5, (): 1.5}, e_0=0.25)
+    assert ham.e_0() == 1.75 and ham.nterms() == 2 and ham.is_individual() and ham.rank() == 2
+    assert not SparseHamiltonian({((0, 1), (2, 0)): 0.5, ((2, 1), (0, 0)): 0.5,
+                                  ((4, 1), (4, 0)): 1.0}).is_individual()
+    it = ham.iht(0.5)
+    assert it.terms()[0][0] == -0.25j and ham.terms()[0][0] == 0.5

@@ -183,3 +183,101 @@ def test_three_body_api_goldens(api, tag):
     out = O.sigma_restricted_123(g, api[f"{tag}_c0"], api[f"{tag}_h1"], api[f"{tag}_h2"],
                                  api[f"{tag}_h3"])
     assert O.rel_err(out, api[f"{tag}_sigma"]) < 1e-12
+
+
+# ---- orbital rotation (transform) and quadratic evolution -------------------
+@pytest.fixture(scope="module")
+def rot(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_transform.npz"))
+
+
+def _sector(z, tag):
+    n, sz, norb = [int(x) for x in z[f"{tag}_meta"]]
+    na = (n + sz) // 2
+    return O.graph(na, n - na, norb), z[f"{tag}_c0"], float(z[f"{tag}_t"][0]), complex(
+        z[f"{tag}_e0"][0])
+
+
+@pytest.mark.parametrize("tag", ["ta", "tb", "tc", "td", "te", "tf"])
+def test_transform_goldens(rot, tag):
+    """Wavefunction.transform / quadratic time_evolve / Diagonal apply + evolve of the
+    reference's public API (recorded by make_golden.py --only transform)"""
+    g, c0, t, e0 = _sector(rot, tag)
+    perm, low, upp, c = O.transform(g, c0, rot[f"{tag}_rot"])
+    assert np.array_equal(perm, rot[f"{tag}_perm"])
+    assert np.allclose(low, rot[f"{tag}_low"], atol=1e-14, rtol=0)
+    assert np.allclose(upp, rot[f"{tag}_upp"], atol=1e-14, rtol=0)
+    assert O.rel_err(c, rot[f"{tag}_transformed"]) < TOL
+    h1, diag = rot[f"{tag}_h1"], rot[f"{tag}_diag"]
+    q = O.time_evolve_quadratic(g, c0, t, h1, e0)
+    assert O.rel_err(q, rot[f"{tag}_quad_evolve"]) < TOL
+    assert O.rel_err(O.evolve_diagonal(g, c0, -1j * t * diag), rot[f"{tag}_evolve_diagonal"]) < TOL
+    assert O.rel_err(O.apply_diagonal(g, c0, diag) + e0 * c0, rot[f"{tag}_diag_apply"]) < TOL
+    assert O.rel_err(O.evolve_diagonal(g, c0, -1j * t * diag) * np.exp(-1j * t * e0),
+                     rot[f"{tag}_diag_evolve"]) < TOL
+    # independent of the snapshot: exact exponential of the dense quadratic Hamiltonian
+    if g.lena * g.lenb <= 400:
+        hm = O.dense_hamiltonian(g, h1, np.zeros((g.norb,) * 4, dtype=np.complex128), e0)
+        w, v = np.linalg.eigh(hm)
+        exact = (v * np.exp(-1j * t * w)) @ (v.conj().T @ c0.reshape(-1))
+        assert O.rel_err(q.reshape(-1), exact) < 1e-11
+
+
+def test_transform_round_trip():
+    """transform(U) realises the rotation U P (P = LU pivot permutation); rotating back with
+    (U P)^H and the same L, U factors, as time_evolve does, is the identity; norms are kept"""
+    from scipy.linalg import expm
+    g = O.graph(2, 1, 4)
+    rng = np.random.default_rng(3)
+    c0 = rng.standard_normal((g.lena, g.lenb)) + 1j * rng.standard_normal((g.lena, g.lenb))
+    assert O.rel_err(O.transform(g, c0, np.identity(4, dtype=np.complex128))[3], c0) < TOL
+    a = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    u = expm(-0.5j * (a + a.conj().T))
+    perm, low, upp, c1 = O.transform(g, c0, u)
+    assert abs(np.linalg.norm(c1) - np.linalg.norm(c0)) < 1e-12
+    assert O.rel_err(c1, c0) > 1e-2
+    back = O.transform(g, c1, (u @ perm).T.conj(), low, upp)[3]
+    assert O.rel_err(back, c0) < 1e-11
+
+
+# ---- SURVEY 8f rank 2: individual n-body operators --------------------------------------------
+@pytest.fixture(scope="module")
+def nbody(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_nbody.npz"))
+
+
+@pytest.mark.parametrize("tag", ["na", "nb", "nc", "nd"])
+def test_individual_nbody_goldens(nbody, tag):
+    """FqeData.apply_individual_nbody / evolve_individual_nbody_nontrivial /
+    evolve_inplace_individual_nbody_trivial of the reference, and an independent brute-force
+    application of the same ladder-operator product"""
+    import ast
+    ops = [ast.literal_eval(str(o)) for o in nbody["ops"]]
+    zc, time = complex(nbody["coeff"][0]), float(nbody["time"][0])
+    n, sz, norb = [int(x) for x in nbody[f"{tag}_meta"]]
+    na = (n + sz) // 2
+    g, c0 = O.graph(na, n - na, norb), nbody[f"{tag}_c0"]
+    seen = 0
+    for k, (da, ua, db, ub) in enumerate(ops):
+        if f"{tag}_apply{k}" not in nbody:
+            continue
+        seen += 1
+        ref = nbody[f"{tag}_apply{k}"]
+        assert np.abs(O.apply_individual_nbody(g, c0, zc, da, ua, db, ub) - ref).max() < 1e-15
+        seq = [(2 * o, 1) for o in da] + [(2 * o, 0) for o in ua] + \
+            [(2 * o + 1, 1) for o in db] + [(2 * o + 1, 0) for o in ub]
+        assert np.abs(O.ladder_sequence_apply(g, c0, seq, zc) - ref).max() < 1e-15
+        if f"{tag}_trivial{k}" in nbody:
+            out = O.evolve_individual_trivial(g, c0, time, zc, da, db)
+            assert O.rel_err(out, nbody[f"{tag}_trivial{k}"]) < TOL
+        else:
+            out = O.evolve_individual_nontrivial(g, c0, time, zc, da, ua, db, ub)
+            assert O.rel_err(out, nbody[f"{tag}_evolve{k}"]) < TOL
+    assert seen >= 6
+    if f"{tag}_w_pair_apply" in nbody:
+        t_op = (zc, [(2, 1), (0, 0)], [(1, 1), (3, 0)])
+        t_dag = (np.conj(zc), [(0, 1), (2, 0)], [(3, 1), (1, 0)])
+        assert O.rel_err(O.sparse_apply(g, c0, [t_op, t_dag], 0.25),
+                         nbody[f"{tag}_w_pair_apply"]) < TOL
+        ev = O.evolve_individual_nontrivial(g, c0, time, zc, [2], [0], [1], [3])
+        assert O.rel_err(ev * np.exp(-0.25j * time), nbody[f"{tag}_w_pair_evolve"]) < TOL
