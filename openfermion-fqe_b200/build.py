@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Build libfqe_b200.so in-tree with nvcc for sm_100a.
 
-    python openfermion-fqe_b200/build.py [--force] [--verbose]
+    python openfermion-fqe_b200/build.py [--force] [--verbose] [--define NAME ... --out PATH]
+
+``--define`` / ``--out`` build an experimental variant next to the product library (A/B runs
+through the ``FQEB_B200_LIB`` environment variable, see fqe_b200/lib/__init__.py).
 
 The library is a plain C-ABI shared object (see include/fqe_b200.h); it does not
 link against torch or Python.  nvcc cross-compiles without a GPU.
@@ -34,18 +37,24 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    if out is None and not force and not stale():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    out = out or OUT
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libfqe_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))
+    argv = sys.argv[1:]
+    defs = [argv[i + 1] for i, a in enumerate(argv) if a == "--define"]
+    outp = argv[argv.index("--out") + 1] if "--out" in argv else None
+    print(build(force="--force" in argv, verbose="--verbose" in argv or "-v" in argv,
+                defines=defs, out=outp))

@@ -57,6 +57,9 @@ constexpr int B_STRIDE_C = 2 * BNR + 8;  // CPLX: [8][264]
 constexpr int B_TILE = 16 * B_STRIDE_R;          // == 8 * B_STRIDE_C
 static_assert(16 * B_STRIDE_R == 8 * B_STRIDE_C, "B tile size mismatch");
 constexpr int COL_ALIGN = 128;  // leading dimensions (complex elements) must be multiples
+#ifndef FQEB_FRAG_PREFETCH
+#define FQEB_FRAG_PREFETCH 3
+#endif
 constexpr int MAX_BM = 144;     // tallest CTA tile of the menu below (operand row padding)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -113,30 +116,83 @@ __device__ __forceinline__ double lds_f64(unsigned base) {
 
 // All DMMAs of one pipeline stage for one warp.  a_base / b_base: shared-memory byte
 // addresses of this lane's first A / B fragment element in the stage.
+//
+// The A fragments rotate through PF register slots and the B fragments through two sets, so
+// that the LDS of the fragment PF-1 steps ahead (and of the next k4 step's B fragments) is in
+// flight while the DMMAs of the current one issue.  With a single A register (the obvious
+// loop) every DMMA pair waits a full shared-memory latency (~30 cycles against 31 cycles of
+// tensor-pipe time for the pair), which the second warp of the sub-partition hides only when
+// the two stay perfectly out of phase: measured 31.1 -> see DESIGN.md.  Loads past kk_count
+// stay inside the stage buffer and are never consumed.
 template <bool CPLX, int WM, int WN, bool RAGGED, int KS = KSTEP>
 __device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], unsigned a_base,
                                           unsigned b_base, int kk_count, int mt_active) {
   constexpr int A_STRIDE = KS + 4;  // shadows the KSTEP=16 constant: row stride of this KS
-  static_for<0, KS / 4>([&](auto kk_c) {
-    constexpr int kk = decltype(kk_c)::value;
-    if (kk < kk_count) {
-      double bf[WN];
+  constexpr int NKK = KS / 4;
+  if constexpr (RAGGED) {
+    static_for<0, NKK>([&](auto kk_c) {
+      constexpr int kk = decltype(kk_c)::value;
+      if (kk < kk_count) {
+        double bf[WN];
+        static_for<0, WN>([&](auto nt_c) {
+          constexpr int nt = decltype(nt_c)::value;
+          constexpr int off = CPLX ? (kk * 2 * B_STRIDE_C + nt * 16) * 8
+                                   : (kk * 4 * B_STRIDE_R + nt * 8) * 8;
+          bf[nt] = lds_f64<off>(b_base);
+        });
+        static_for<0, WM>([&](auto mt_c) {
+          constexpr int mt = decltype(mt_c)::value;
+          if (mt < mt_active) {
+            const double af = lds_f64<(mt * 8 * A_STRIDE + kk * 4) * 8>(a_base);
+#pragma unroll
+            for (int nt = 0; nt < WN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
+          }
+        });
+      }
+    });
+  } else {
+    // A-fragment slots in flight (one less next to 144 accumulator registers)
+    constexpr int PF = (WM * WN * 4 > 140 && FQEB_FRAG_PREFETCH > 2) ? 2 : FQEB_FRAG_PREFETCH;
+    static_assert(PF >= 1 && PF <= WM, "prefetch depth");
+    double af[PF];
+    double bf[2][WN];
+    auto load_b = [&](auto kk_c, auto set_c) {
+      constexpr int kk = decltype(kk_c)::value;
+      constexpr int set = decltype(set_c)::value;
       static_for<0, WN>([&](auto nt_c) {
         constexpr int nt = decltype(nt_c)::value;
         constexpr int off = CPLX ? (kk * 2 * B_STRIDE_C + nt * 16) * 8
                                  : (kk * 4 * B_STRIDE_R + nt * 8) * 8;
-        bf[nt] = lds_f64<off>(b_base);
+        bf[set][nt] = lds_f64<off>(b_base);
       });
-      static_for<0, WM>([&](auto mt_c) {
-        constexpr int mt = decltype(mt_c)::value;
-        if (!RAGGED || mt < mt_active) {
-          const double af = lds_f64<(mt * 8 * A_STRIDE + kk * 4) * 8>(a_base);
+    };
+    // prologue: B fragments of k4 step 0 and the first PF A fragments
+    load_b(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+    static_for<0, PF>([&](auto i_c) {
+      constexpr int i = decltype(i_c)::value;
+      af[i] = lds_f64<(i * 8 * A_STRIDE) * 8>(a_base);
+    });
+    static_for<0, NKK>([&](auto kk_c) {
+      constexpr int kk = decltype(kk_c)::value;
+      if (kk < kk_count) {
+        if constexpr (kk + 1 < NKK)
+          load_b(std::integral_constant<int, kk + 1>{}, std::integral_constant<int, (kk + 1) & 1>{});
+        static_for<0, WM>([&](auto mt_c) {
+          constexpr int mt = decltype(mt_c)::value;
+          constexpr int slot = (kk * WM + mt) % PF;
 #pragma unroll
-          for (int nt = 0; nt < WN; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
-        }
-      });
-    }
-  });
+          for (int nt = 0; nt < WN; ++nt)
+            dmma884(acc[mt][nt][0], acc[mt][nt][1], af[slot], bf[kk & 1][nt]);
+          // refill the slot with the fragment PF steps ahead (next k4 step past the last row)
+          constexpr int nxt = mt + PF;
+          if constexpr (nxt < WM)
+            af[slot] = lds_f64<(nxt * 8 * A_STRIDE + kk * 4) * 8>(a_base);
+          else if constexpr (kk + 1 < NKK)
+            af[slot] = lds_f64<((nxt - WM) * 8 * A_STRIDE + (kk + 1) * 4) * 8>(a_base);
+        });
+      }
+    });
+  }
 }
 
 // CTA tile = BM x 128 real elements, 8 warps arranged WARPS_M x (8/WARPS_M); each
@@ -327,9 +383,21 @@ k_dgemm(const double *__restrict__ A, int lda, int a_col0, const double2 *__rest
   cp_async_wait<0>();
 }
 
+// epilogue store of one complex element of E (streaming: E is read back once, by the scatter)
+__device__ __forceinline__ void store_e(double2 *p, double2 v) {
+#if defined(FQEB_EXP_NOSTORE)
+  if (v.x == 1.2345e300) __stcs(p, v);   // experiment: measure the epilogue's cost
+#elif defined(FQEB_EXP_PLAINSTORE)
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+
 // ---- warp-specialised variant --------------------------------------------------------
-// Same tiles, same math, different plumbing: two PRODUCER warps (one streams A tiles,
-// one streams D tiles, cp.async) feed eight CONSUMER warps through a ring of STAGES
+// Same tiles, same math, different plumbing: one PRODUCER warpgroup (two warps stream A
+// tiles, two stream D tiles, cp.async) feeds eight CONSUMER warps (two warpgroups) through a
+// ring of STAGES
 // shared-memory slots guarded by mbarriers (full[s]: data landed, empty[s]: all
 // consumer warps are done with slot s).  There is no CTA-wide barrier in the main
 // loop: consumer warps drift apart instead of hitting their non-tensor phases (fragment
@@ -358,7 +426,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive(unsigned addr) {
 }
 
 template <bool CPLX, int WARPS_M, int WM, int WN, bool RAGGED, int KS, int NST>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__restrict__ B,
            int64_t ldb, double2 *__restrict__ E, int64_t lde, int m_valid, int nrows_out,
            int k_valid, int nmb, int64_t ntiles) {
@@ -385,7 +453,7 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + s * 8, 64);   // 2 producer warps, one arrive per lane
+      mbar_init(bar_full + s * 8, 128);  // 4 producer warps, one arrive per lane
       mbar_init(bar_empty + s * 8, 8);   // one arrive per consumer warp
     }
   }
@@ -398,9 +466,12 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
   int mb = (int)(blockIdx.x % nmb);
   int64_t nb = blockIdx.x / nmb;
 
-  if (warp >= 8) {
-    // =========================== producers ===========================================
-    const bool loads_a = (warp == 8);
+  if (warp < 4) {
+    // =========================== producers (warpgroup 0) =============================
+    // give the registers this warpgroup does not need to the two consumer warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    const bool loads_a = (warp < 2);
+    const int half = warp & 1;                  // two warps share each operand
     constexpr int B_CHUNKS = CPLX ? 128 : 64;   // 16-byte chunks per B row
     constexpr int B_STRIDE = CPLX ? B_STRIDE_C : B_STRIDE_R;
     constexpr int B_SUB = B_CHUNKS / 32;        // lane-strided pieces per B row
@@ -425,13 +496,13 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
       const unsigned sbase = stage * STAGE_BYTES;
       if (loads_a) {
 #pragma unroll 8
-        for (int i = 0; i < BM / A_RPP; ++i)
+        for (int i = half; i < BM / A_RPP; i += 2)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
                            a_dst0 + sbase + i * A_RPP * A_STRIDE * 8),
                        "l"(a_src + (int64_t)(i * A_RPP) * lda));
       } else {
 #pragma unroll 8
-        for (int i = 0; i < B_ROWS_STAGE * B_SUB; ++i) {
+        for (int i = half; i < B_ROWS_STAGE * B_SUB; i += 2) {
           const int r = i / B_SUB, j = i % B_SUB;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
                            b_dst0 + sbase + (r * B_STRIDE + j * 64) * 8),
@@ -462,10 +533,12 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
     return;
   }
 
-  // ============================= consumers =============================================
+  // ============================= consumers (warpgroups 1, 2) ============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
+  const int cw = warp - 4;
   const int g = lane >> 2, tg = lane & 3;
-  const int wm0 = (warp / WARPS_N) * (WM * 8);
-  const int wn0 = (warp % WARPS_N) * (WN * 8);
+  const int wm0 = (cw / WARPS_N) * (WM * 8);
+  const int wn0 = (cw % WARPS_N) * (WN * 8);
   const unsigned a_frag_off = ((wm0 + g) * A_STRIDE + tg) * 8;
   const unsigned b_frag_off =
       (A_TILE + (CPLX ? (tg >> 1) * B_STRIDE_C + (wn0 + g) * 2 + (tg & 1)
@@ -507,8 +580,8 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
               double2 *erow = E + (int64_t)kl * lde + n0 + wn0 + 2 * tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt) {
-                __stcs(erow + nt * 8, make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]));
-                __stcs(erow + nt * 8 + 1, make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]));
+                store_e(erow + nt * 8, make_double2(acc[2 * p][nt][0], acc[2 * p + 1][nt][0]));
+                store_e(erow + nt * 8 + 1, make_double2(acc[2 * p][nt][1], acc[2 * p + 1][nt][1]));
               }
             }
           }
@@ -522,7 +595,7 @@ k_dgemm_ws(const double *__restrict__ A, int lda, int a_col0, const double2 *__r
               double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
               for (int nt = 0; nt < WN; ++nt)
-                __stcs(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+                store_e(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
             }
           }
         }
@@ -576,7 +649,7 @@ static int launch_ws(const fqeb_op *op, const double *d_A, int a_col0, const dou
   int64_t grid = sm_count();
   if (grid > nmb) grid -= grid % nmb;
   if (grid > tiles) grid = tiles;
-  kern<<<(unsigned)grid, 320, SMEM, st>>>(d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
+  kern<<<(unsigned)grid, 384, SMEM, st>>>(d_A, op->Kp, a_col0, (const double2 *)d_dvec, ldd,
                                           (double2 *)d_evec, lde, m_valid, op->np, k_valid, nmb,
                                           tiles);
   FQEB_CHECK_LAUNCH();

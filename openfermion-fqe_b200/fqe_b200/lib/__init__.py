@@ -12,7 +12,8 @@ from ctypes import (POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfqe_b200.so")
+# FQEB_B200_LIB points at an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("FQEB_B200_LIB") or os.path.join(_HERE, "libfqe_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE, ERR_CONVERGE = range(6)
 OP_REAL, OP_IMAG, OP_COMPLEX = 0, 1, 2
