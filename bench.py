@@ -236,7 +236,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
 
     for _ in range(args.warmup):
         sigma = step()
-    del sigma
+    sigma = None
     barrier()
     lib.fqeb_profile_enable(1)
     ms3, cnt3 = (ctypes.c_double * 3)(), (ctypes.c_int64 * 3)()
