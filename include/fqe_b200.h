@@ -114,6 +114,11 @@ enum { FQEB_OP_FLAG_FULL_PAIR_SPACE = 1 };
 int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_h2p, int flags,
                       fqeb_op **out);
 int fqeb_op_destroy(fqeb_op *op);
+/* Non-blocking destroy: device buffers are released in stream order on `stream`, i.e. after the
+ * kernels already enqueued there that may still read the operator; fqeb_op_destroy waits for
+ * the whole device instead.  Creating an operator never waits for running kernels either
+ * (uploads use an internal stream). */
+int fqeb_op_destroy_async(fqeb_op *op, void *stream);
 int fqeb_op_kind(const fqeb_op *op, int *kind);
 /* Size of the pair space the contraction runs over and whether it is compressed:
  * norb^2, or norb(norb+1)/2 when h2p[ij,kl] == h2p[ji,kl] == h2p[ij,lk] exactly

@@ -40,6 +40,36 @@ int sm_count() {
   return cached[dev];
 }
 
+// Small host -> device uploads (operator tables) go through an internal non-blocking stream
+// and a stream-ordered allocation, so that preparing the next operator neither waits for nor
+// stalls the sigma build that is still running on the caller's stream (a plain cudaMemcpy
+// synchronises with the legacy default stream, cudaMalloc / cudaFree with the whole device).
+static cudaStream_t upload_stream() {
+  static cudaStream_t streams[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev] &&
+      cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess)
+    streams[dev] = nullptr;
+  return streams[dev];
+}
+
+int upload_alloc(void **d_ptr, const void *h_src, size_t bytes) {
+  cudaStream_t st = upload_stream();
+  FQEB_REQUIRE(st != nullptr, "cannot create the upload stream");
+  *d_ptr = nullptr;
+  FQEB_CUDA(cudaMallocAsync(d_ptr, bytes, st));
+  if (h_src) FQEB_CUDA(cudaMemcpyAsync(*d_ptr, h_src, bytes, cudaMemcpyHostToDevice, st));
+  return FQEB_OK;
+}
+
+int upload_finish() {
+  cudaStream_t st = upload_stream();
+  FQEB_REQUIRE(st != nullptr, "cannot create the upload stream");
+  FQEB_CUDA(cudaStreamSynchronize(st));
+  return FQEB_OK;
+}
+
 }  // namespace fqeb
 
 extern "C" const char *fqeb_last_error(void) { return fqeb::g_err; }

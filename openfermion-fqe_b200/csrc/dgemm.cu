@@ -1111,12 +1111,8 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
     fqeb_op_destroy(op);
     return code;
   };
-  if (cudaMalloc(&op->d_h1, sizeof(double) * 2 * npair) != cudaSuccess ||
-      cudaMemcpy(op->d_h1, h_h1p, sizeof(double) * 2 * npair, cudaMemcpyHostToDevice) !=
-          cudaSuccess) {
-    set_error("fqeb_op_create: cannot upload h1: %s", cudaGetErrorString(cudaGetLastError()));
+  if (upload_alloc((void **)&op->d_h1, h_h1p, sizeof(double) * 2 * npair) != FQEB_OK)
     return fail(FQEB_ERR_CUDA);
-  }
   auto h2 = [&](int i, int j, int k, int l, int part) {
     return h_h2p[2 * ((((size_t)i * norb + j) * norb + k) * norb + l) + part];
   };
@@ -1170,12 +1166,9 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
         rowmap[p] = p;
       }
     }
-    if (cudaMalloc(&op->d_pairs, sizeof(int32_t) * tab.size()) != cudaSuccess ||
-        cudaMemcpy(op->d_pairs, tab.data(), sizeof(int32_t) * tab.size(),
-                   cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error("fqeb_op_create: cannot upload pair tables");
+    if (upload_alloc((void **)&op->d_pairs, tab.data(), sizeof(int32_t) * tab.size()) != FQEB_OK ||
+        upload_finish() != FQEB_OK)   // tab goes out of scope
       return fail(FQEB_ERR_CUDA);
-    }
     op->d_rowmap = op->d_pairs + 2 * np;
   }
   if (op->has_h2) {
@@ -1221,13 +1214,9 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
       for (int c = 0; c < np; ++c)
         for (int d = 0; d < np; ++d) a[(size_t)c * op->Kp + d] = elem(c, d, off);
     }
-    if (cudaMalloc(&op->d_A, sizeof(double) * a.size()) != cudaSuccess ||
-        cudaMemcpy(op->d_A, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice) !=
-            cudaSuccess) {
-      set_error("fqeb_op_create: cannot upload h2 operand: %s",
-                cudaGetErrorString(cudaGetLastError()));
+    if (upload_alloc((void **)&op->d_A, a.data(), sizeof(double) * a.size()) != FQEB_OK ||
+        upload_finish() != FQEB_OK)   // a goes out of scope
       return fail(FQEB_ERR_CUDA);
-    }
   }
   // Can the one-body term be absorbed into the contraction operand,
   //     A[c, d] += h1'[pair(c)] / n_elec   for every diagonal pair d = (k, k)
@@ -1261,6 +1250,7 @@ extern "C" int fqeb_op_create_ex(int norb, const double *h_h1p, const double *h_
     memcpy(op->h_h2p, h_h2p, sizeof(double) * 2 * (size_t)npair * npair);
     op->fused_cache = new std::map<int, double *>();
   }
+  if (upload_finish() != FQEB_OK) return fail(FQEB_ERR_CUDA);
   *out = op;
   return FQEB_OK;
 }
@@ -1308,28 +1298,41 @@ int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A) {
       for (int d = 0; d < np; ++d) a[(size_t)c * op->Kp + d] = elem(c, d, off);
   }
   double *dev = nullptr;
-  FQEB_CUDA(cudaMalloc(&dev, sizeof(double) * a.size()));
-  FQEB_CUDA(cudaMemcpy(dev, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice));
+  int rc = upload_alloc((void **)&dev, a.data(), sizeof(double) * a.size());
+  if (rc == FQEB_OK) rc = upload_finish();
+  if (rc != FQEB_OK) return rc;
   (*cache)[n_elec] = dev;
   *d_A = dev;
   return FQEB_OK;
 }
 }  // namespace fqeb
 
-extern "C" int fqeb_op_destroy(fqeb_op *op) {
+// Device buffers are returned with cudaFreeAsync on `stream`: the release is ordered after the
+// work already enqueued there (the kernels that may still read the operator) and does not
+// synchronise the device.
+extern "C" int fqeb_op_destroy_async(fqeb_op *op, void *stream) {
   if (!op) return FQEB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   if (op->fused_cache) {
     auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
-    for (auto &kv : *cache) cudaFree(kv.second);
+    for (auto &kv : *cache) cudaFreeAsync(kv.second, st);
     delete cache;
   }
   free(op->h_h1p);
   free(op->h_h2p);
-  if (op->d_A) cudaFree(op->d_A);
-  if (op->d_h1) cudaFree(op->d_h1);
-  if (op->d_pairs) cudaFree(op->d_pairs);
+  if (op->d_A) cudaFreeAsync(op->d_A, st);
+  if (op->d_h1) cudaFreeAsync(op->d_h1, st);
+  if (op->d_pairs) cudaFreeAsync(op->d_pairs, st);
   free(op);
   return FQEB_OK;
+}
+
+// Blocking variant: waits for the device, so the operator may be destroyed whatever stream
+// used it last.
+extern "C" int fqeb_op_destroy(fqeb_op *op) {
+  if (!op) return FQEB_OK;
+  cudaDeviceSynchronize();
+  return fqeb_op_destroy_async(op, nullptr);
 }
 
 extern "C" int fqeb_op_kind(const fqeb_op *op, int *kind) {

@@ -46,6 +46,10 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 int require_device();  // FQEB_OK or FQEB_ERR_NODEVICE (with message)
 int sm_count();
+// stream-ordered allocation + upload on the internal non-blocking stream; upload_finish()
+// blocks the host until every upload issued so far has landed
+int upload_alloc(void **d_ptr, const void *h_src, size_t bytes);
+int upload_finish();
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

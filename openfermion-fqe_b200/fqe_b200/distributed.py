@@ -94,3 +94,69 @@ def sharded_apply_host(sector, op, host_coeff: torch.Tensor, host_sigma: torch.T
     sigma = sharded_apply(sector, op, mode)
     host_sigma[r0:r1].copy_(sigma[r0:r1], non_blocking=True)
     torch.cuda.current_stream().synchronize()
+
+
+class HostApplyStream:
+    """A stream of independent end-to-end sigma builds with HOST buffers, software-pipelined:
+    the upload of build k+1 and the download of build k-1 run on their own CUDA streams while
+    build k computes (double-buffered device coefficients).  Every build still moves its own
+    input host -> device and its own result device -> host; only the waiting is overlapped.
+
+        pipe = HostApplyStream(sector, mode="det")
+        for c_host, s_host in batches:          # pinned complex128 [lena, lenb] tensors
+            pipe.submit(op, c_host, s_host)
+        pipe.drain()                            # all results have landed in their s_host
+
+    With more than one rank each rank uploads / downloads only its row slice (as
+    ``sharded_apply_host``); the exchange and the all-reduce stay on the compute stream."""
+
+    def __init__(self, sector, mode: str = "det", depth: int = 2):
+        from fqe_b200.fqe_data import FqeData
+        self.mode = mode
+        self.world = dist.get_world_size() if (dist.is_available() and
+                                               dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.slices = split_even(sector.lena(), self.world)
+        self.s_in = torch.cuda.Stream()
+        self.s_out = torch.cuda.Stream()
+        self.slots = []
+        for _ in range(depth):
+            data = FqeData(sector.nalpha(), sector.nbeta(), sector.norb(), sector.get_fcigraph())
+            self.slots.append({"data": data, "sigma": None, "h2d": torch.cuda.Event(),
+                               "done": torch.cuda.Event(), "d2h": torch.cuda.Event(),
+                               "used": False})
+        self.count = 0
+
+    def submit(self, op, host_coeff: torch.Tensor, host_sigma: torch.Tensor) -> None:
+        slot = self.slots[self.count % len(self.slots)]
+        self.count += 1
+        cur = torch.cuda.current_stream()
+        r0, r1 = self.slices[self.rank]
+        data = slot["data"]
+        if slot["used"]:
+            slot["d2h"].synchronize()          # the result that lived in this slot is home
+            self.s_in.wait_event(slot["done"])  # and its coefficients are no longer read
+        with torch.cuda.stream(self.s_in):
+            data.coeff[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
+            slot["h2d"].record(self.s_in)
+        cur.wait_event(slot["h2d"])
+        if self.world > 1:
+            for src, (s0, s1) in enumerate(self.slices):
+                if s1 > s0:
+                    dist.broadcast(torch.view_as_real(data.coeff[s0:s1]), src=src)
+        sigma = sharded_apply(data, op, self.mode)
+        slot["done"].record(cur)
+        sigma.record_stream(self.s_out)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["done"])
+            host_sigma[r0:r1].copy_(sigma[r0:r1], non_blocking=True)
+            slot["d2h"].record(self.s_out)
+        slot["sigma"] = sigma
+        slot["used"] = True
+
+    def drain(self) -> None:
+        for slot in self.slots:
+            if slot["used"]:
+                slot["d2h"].synchronize()
+                slot["sigma"] = None
+        torch.cuda.current_stream().synchronize()

@@ -180,13 +180,23 @@ class DenseOperator:
 
     @property
     def handle(self) -> ctypes.c_void_p:
+        """Native handle.  Every access notes the current CUDA stream: the device buffers are
+        released in that stream's order when the operator is dropped, i.e. after the kernels
+        that were handed this handle, without synchronising the device."""
+        self._streams = getattr(self, "_streams", set())
+        if torch.cuda.is_available():
+            self._streams.add(_stream())
         return self._handle
 
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value:
             try:
-                _lib.load().fqeb_op_destroy(h)
+                streams = getattr(self, "_streams", set())
+                if len(streams) == 1:
+                    _lib.load().fqeb_op_destroy_async(h, next(iter(streams)))
+                else:   # never used, or used on several streams: wait for the device
+                    _lib.load().fqeb_op_destroy(h)
             except Exception:
                 pass
             self._handle = None

@@ -47,6 +47,7 @@ SIGNATURES = {
     "fqeb_op_create": (c_int, [c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "fqeb_op_create_ex": (c_int, [c_int, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "fqeb_op_destroy": (c_int, [c_void_p]),
+    "fqeb_op_destroy_async": (c_int, [c_void_p, c_void_p]),
     "fqeb_op_kind": (c_int, [c_void_p, POINTER(c_int)]),
     "fqeb_op_pair_space": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "fqeb_make_dvec": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,

@@ -301,3 +301,27 @@ def test_one_body_shards():
     assert O.rel_err(rows.cpu().numpy(), ref) < TOL
     pairs = d.apply_operator(op, pair_range=(0, 20)) + d.apply_operator(op, pair_range=(20, npair))
     assert O.rel_err(pairs.cpu().numpy(), ref) < TOL
+
+
+def test_host_apply_stream_pipelines_independent_builds():
+    """HostApplyStream: five builds on different inputs through two device slots; every
+    result equals the unpipelined apply of its own input"""
+    from fqe_b200 import synth
+    from fqe_b200.distributed import HostApplyStream
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    na, nb, norb = 4, 4, 8
+    h1, h2 = synth.integrals(norb, "real8")
+    op = DenseOperator(norb, h1, h2)
+    g = O.graph(na, nb, norb)
+    d = FqeData(na, nb, norb)
+    ins = [torch.from_numpy(synth.state(g.lena, g.lenb, seed=100 + k)).pin_memory()
+           for k in range(5)]
+    outs = [torch.empty((g.lena, g.lenb), dtype=torch.complex128).pin_memory() for _ in range(5)]
+    pipe = HostApplyStream(d)
+    for c, s in zip(ins, outs):
+        pipe.submit(op, c, s)
+    pipe.drain()
+    for c, s in zip(ins, outs):
+        d.set_wfn(strategy="from_data", raw_data=c.numpy())
+        ref = d.apply_operator(op).cpu().numpy()
+        assert O.rel_err(s.numpy(), ref) < 1e-14
