@@ -569,6 +569,58 @@ class FqeData:
                   self._check_coeff(data).data_ptr(), _stream())
         return data
 
+    # ---- reduced density matrices (fqe_data.py:1668-1838) ------------------------------------
+    _rdm_block_bytes = 1 << 32
+
+    def _rdm_blocks(self, bradata: Optional['FqeData'], want2: bool):
+        """sum over alpha-row blocks of  T[ij] = <D_bra[ij] | C>  and  G[ij,kl] =
+        <D_bra[ij] | D_ket[kl]>, D = E_ij applied to the state (gather kernel); the two small
+        reductions over the determinant index are library GEMMs (cuBLAS through torch)."""
+        dev = _require_cuda()
+        bra = self if bradata is None else bradata
+        if bra.lena() != self.lena() or bra.lenb() != self.lenb() or bra.norb() != self.norb():
+            raise ValueError("bra and ket sectors differ")
+        norb, la, lb = self.norb(), self.lena(), self.lenb()
+        npair = norb * norb
+        # two D blocks of at most _rdm_block_bytes (4 GB) each
+        rows = max(1, min(la, self._rdm_block_bytes // max(1, 16 * npair * lb)))
+        t1 = torch.zeros(npair, dtype=torch.complex128, device=dev)
+        g2 = torch.zeros((npair, npair), dtype=torch.complex128, device=dev) if want2 else None
+        ket_c, bra_c = self._check_coeff(self.coeff), self._check_coeff(bra.coeff)
+        for r0 in range(0, la, rows):
+            nr = min(rows, la - r0)
+            ld = nr * lb
+            dket = torch.empty((npair, ld), dtype=torch.complex128, device=dev)
+            _lib.call("fqeb_make_dvec", self._core.handle, ket_c.data_ptr(), dket.data_ptr(), ld,
+                      r0, nr, 0, npair, _stream())
+            if bra is self:
+                dbra = dket
+            else:
+                dbra = torch.empty((npair, ld), dtype=torch.complex128, device=dev)
+                _lib.call("fqeb_make_dvec", self._core.handle, bra_c.data_ptr(), dbra.data_ptr(),
+                          ld, r0, nr, 0, npair, _stream())
+            t1 += dbra.conj() @ ket_c[r0:r0 + nr].reshape(-1)
+            if want2:
+                g2 += dbra.conj() @ dket.transpose(0, 1)
+            del dket, dbra
+        return t1.cpu().numpy().reshape(norb, norb), \
+            (g2.cpu().numpy().reshape((norb,) * 4) if want2 else None)
+
+    def rdm1(self, bradata: Optional['FqeData'] = None) -> Tuple[numpy.ndarray]:
+        """(rdm1,) with rdm1[i,j] = <bra| a+_i a_j |ket>, spin-summed (fqe_data.py:1668-1724)"""
+        t1, _ = self._rdm_blocks(bradata, False)
+        return (numpy.transpose(t1),)
+
+    def rdm12(self, bradata: Optional['FqeData'] = None) -> Tuple[numpy.ndarray, numpy.ndarray]:
+        """(rdm1, rdm2) with rdm2[i,j,k,l] = <bra| a+_i a+_j a_k a_l |ket>
+        (fqe_data.py:1726-1807; one algorithm for every filling)."""
+        t1, g2 = self._rdm_blocks(bradata, True)
+        rdm1 = numpy.transpose(t1)
+        rdm2 = -g2.transpose(1, 2, 0, 3)
+        for i in range(self.norb()):
+            rdm2[:, i, i, :] += rdm1
+        return rdm1, numpy.ascontiguousarray(rdm2)
+
     # ---- individual n-body operators (fqe_data.py:1558-1653, 2385-2580) --------------------
     @staticmethod
     def _op_arrays(dag, undag, norb: int):

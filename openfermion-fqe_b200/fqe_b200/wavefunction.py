@@ -15,6 +15,8 @@ handled; anything else raises ``NotImplementedError`` rather than falling back.
 """
 import copy
 import math
+import os
+import pickle
 from typing import Dict, KeysView, List, Optional, Tuple, Union
 
 import numpy
@@ -404,6 +406,41 @@ class Wavefunction:
             final_wfn.scale(numpy.exp(-1.j * time * hamil.e_0()))
         self.last_expansion_order = getattr(work_wfn, "last_expansion_order", 0)
         return final_wfn
+
+    # ---- RDMs, save / read (wavefunction.py:1357-1415, 726-765) -------------------------------
+    def _compute_rdm(self, rank: int, brawfn: Optional['Wavefunction'] = None):
+        """Tuple of spin-summed RDMs up to ``rank`` (1 or 2), summed over the sectors"""
+        assert 0 < rank < 5
+        if rank > 2:
+            raise NotImplementedError("3- and 4-particle RDMs are outside the B200 hot path")
+        out = None
+        for key, sector in self._civec.items():
+            assert brawfn is None or key in brawfn.sectors()
+            bra = None if brawfn is None else brawfn._civec[key]
+            tmp = sector.rdm1(bra) if rank == 1 else sector.rdm12(bra)
+            out = tmp if out is None else tuple(a + b for a, b in zip(out, tmp))
+        return out
+
+    def save(self, filename: str, path: str = os.getcwd()) -> None:
+        """Pickle [conserved, norb, [key, complex128 ndarray]...] (own format: the reference
+        pickles its FqeData objects, which only the reference package can load)."""
+        data = [dict(self._conserved), self._norb]
+        for key, sec in self._civec.items():
+            data.append([key, sec.to_numpy()])
+        with open(os.path.join(path, filename), 'w+b') as fh:
+            pickle.dump(data, fh)
+
+    def read(self, filename: str, path: str = os.getcwd()) -> None:
+        with open(os.path.join(path, filename), 'r+b') as fh:
+            data = pickle.load(fh)
+        self._conserved, self._norb = dict(data[0]), data[1]
+        self._civec = {}
+        for key, arr in data[2:]:
+            nele, m_s = key
+            na, nb = alpha_beta_electrons(nele, m_s)
+            sec = FqeData(na, nb, self._norb)
+            sec.set_wfn(strategy='from_data', raw_data=arr)
+            self._civec[(nele, m_s)] = sec
 
     # ---- individual n-body operators (wavefunction.py:1135-1328) ---------------------------
     def _operator_lists(self, alpha, beta):

@@ -703,6 +703,22 @@ def ladder_sequence_apply(g: OracleGraph, coeff: np.ndarray, ops, zc: complex = 
     return out
 
 
+# --------------------------------------------------------------------------
+# 8f rank 4: 1- and 2-particle (transition) RDMs  (fqe_data.py:1668-1838)
+# --------------------------------------------------------------------------
+def rdm12(g: OracleGraph, ket: np.ndarray, bra: np.ndarray = None):
+    """FqeData._rdm12_halffilling, Python branch (fqe_data.py:1764-1780):
+    rdm1[i,j] = <bra| a+_i a_j |ket>,  rdm2[i,j,k,l] = <bra| a+_i a+_j a_k a_l |ket>."""
+    dvec = dvec_spatial(g, ket)
+    dvec2 = dvec if bra is None else dvec_spatial(g, bra)
+    out1 = np.transpose(np.tensordot(dvec2.conj(), ket))
+    out2 = np.transpose(np.tensordot(dvec2.conj(), dvec, axes=((2, 3), (2, 3))),
+                        axes=(1, 2, 0, 3)) * (-1.0)
+    for i in range(g.norb):
+        out2[:, i, i, :] += out1[:, :]
+    return out1, out2
+
+
 def dense_hamiltonian(g, h1, h2, e0=0.0):
     """Column-by-column H matrix, as tests/evolution_test.py:527-594 builds it."""
     dim = g.lena * g.lenb

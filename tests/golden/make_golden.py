@@ -26,6 +26,7 @@ Outputs (all small, committed):
                                 (`--only transform` regenerates just this file)
     ref_nbody.npz               SURVEY 8f rank 2: individual n-body apply / exact evolution through
                                 FqeData and through Wavefunction + SparseHamiltonian (`--only nbody`)
+    ref_rdm.npz                 SURVEY 8f rank 4: FqeData.rdm1 / rdm12, plain and transition (`--only rdm`)
 """
 import os
 import shutil
@@ -227,6 +228,30 @@ def nbody_goldens(fqe):
     print("ref_nbody.npz", os.path.getsize(os.path.join(HERE, "ref_nbody.npz")), "bytes")
 
 
+def rdm_goldens(fqe):
+    """1- and 2-particle (transition) RDMs of single sectors, FqeData.rdm1 / rdm12
+    (SURVEY 8f rank 4); covers the half-filling and the low-filling algorithm."""
+    out = {}
+    for tag, n, sz, norb in [("ra", 4, 0, 4), ("rb", 5, 1, 6), ("rc", 2, 0, 8), ("rd", 3, -1, 5),
+                             ("re", 6, 0, 6)]:
+        rng = np.random.default_rng(20260800 + 100 * norb + ord(tag[1]))
+        wfn = fqe.Wavefunction([[n, sz, norb]])
+        shape = wfn.get_coeff((n, sz)).shape
+        ket, bra = rand_state(shape, rng), rand_state(shape, rng)
+        wfn.set_wfn(strategy="from_data", raw_data={(n, sz): ket.copy()})
+        bwfn = fqe.Wavefunction([[n, sz, norb]])
+        bwfn.set_wfn(strategy="from_data", raw_data={(n, sz): bra.copy()})
+        sec, bsec = wfn.sector((n, sz)), bwfn.sector((n, sz))
+        out[f"{tag}_meta"] = np.array([n, sz, norb], dtype=np.int64)
+        out[f"{tag}_ket"], out[f"{tag}_bra"] = ket, bra
+        (out[f"{tag}_rdm1"],) = sec.rdm1()
+        (out[f"{tag}_trdm1"],) = sec.rdm1(bsec)
+        out[f"{tag}_rdm12_1"], out[f"{tag}_rdm12_2"] = sec.rdm12()
+        out[f"{tag}_trdm12_1"], out[f"{tag}_trdm12_2"] = sec.rdm12(bsec)
+    np.savez_compressed(os.path.join(HERE, "ref_rdm.npz"), **out)
+    print("ref_rdm.npz", os.path.getsize(os.path.join(HERE, "ref_rdm.npz")), "bytes")
+
+
 def main():
     src = build_reference()
     install_stubs()
@@ -238,7 +263,7 @@ def main():
 
     fqe.settings.use_accelerated_code = True
     if "--only" in sys.argv:
-        {"transform": transform_goldens, "nbody": nbody_goldens}[
+        {"transform": transform_goldens, "nbody": nbody_goldens, "rdm": rdm_goldens}[
             sys.argv[sys.argv.index("--only") + 1]](fqe)
         return
 
@@ -395,6 +420,7 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
     transform_goldens(fqe)
     nbody_goldens(fqe)
+    rdm_goldens(fqe)
 
 
 if __name__ == "__main__":

@@ -281,3 +281,17 @@ def test_individual_nbody_goldens(nbody, tag):
                          nbody[f"{tag}_w_pair_apply"]) < TOL
         ev = O.evolve_individual_nontrivial(g, c0, time, zc, [2], [0], [1], [3])
         assert O.rel_err(ev * np.exp(-0.25j * time), nbody[f"{tag}_w_pair_evolve"]) < TOL
+
+
+# ---- RDMs ------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["ra", "rb", "rc", "rd", "re"])
+def test_rdm_goldens(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, "ref_rdm.npz"))
+    n, sz, norb = [int(x) for x in z[f"{tag}_meta"]]
+    na = (n + sz) // 2
+    g = O.graph(na, n - na, norb)
+    r1, r2 = O.rdm12(g, z[f"{tag}_ket"])
+    t1, t2 = O.rdm12(g, z[f"{tag}_ket"], z[f"{tag}_bra"])
+    for got, key in ((r1, "rdm1"), (r1, "rdm12_1"), (r2, "rdm12_2"), (t1, "trdm1"),
+                     (t1, "trdm12_1"), (t2, "trdm12_2")):
+        assert O.rel_err(got, z[f"{tag}_{key}"]) < TOL
