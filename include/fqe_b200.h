@@ -280,6 +280,22 @@ int fqeb_axpy_norm2(int64_t n, double cr, double ci, const double *d_work,
                     double *d_evol, void *d_scratch, double *h_out,
                     void *stream);
 
+/* ------------------------------------------------------------------------
+ * a13  Taylor propagator, whole recurrence in one call
+ * replaces the loop of Wavefunction.apply_generated_unitary(algo='taylor')
+ * (wavefunction.py:548-567) for one sector: on entry d_evol holds C, on exit
+ * sum_k op^k C / k!, with `op` created from the tensors of -i*t*H
+ * (Hamiltonian.iht).  d_work, d_next: scratch of the size of C; d_workspace as
+ * for fqeb_sigma_restricted; d_scratch: fqeb_reduce_scratch_bytes().  Stops when
+ * ||op^k C|| / k! < accuracy and stores k in *nterms; FQEB_ERR_CONVERGE when
+ * max_terms is reached (the reference raises RuntimeError there).  The e_0
+ * phase is the caller's (wavefunction.py:600-601).
+ * ------------------------------------------------------------------------ */
+int fqeb_taylor(const fqeb_graph *g, const fqeb_op *op, double *d_evol,
+                double *d_work, double *d_next, void *d_workspace,
+                size_t workspace_bytes, void *d_scratch, double accuracy,
+                int max_terms, int *nterms, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

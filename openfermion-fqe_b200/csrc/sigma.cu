@@ -251,6 +251,47 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   return FQEB_OK;
 }
 
+// Taylor propagator, whole recurrence on the device (reference wavefunction.py:548-567):
+//   evol = sum_k op^k / k! |C>,  op prepared from the tensors of -i*t*H (Hamiltonian.iht).
+// The loop stops when ||op^k C|| / k! < accuracy; running into max_terms is an error, as the
+// reference raises RuntimeError("maximum taylor expansion limit reached").
+extern "C" int fqeb_taylor(const fqeb_graph *g, const fqeb_op *op, double *d_evol, double *d_work,
+                           double *d_next, void *d_workspace, size_t workspace_bytes,
+                           void *d_scratch, double accuracy, int max_terms, int *nterms,
+                           void *stream) {
+  int rc = require_device();
+  if (rc != FQEB_OK) return rc;
+  FQEB_REQUIRE(g && op && d_evol && d_work && d_next && d_scratch && nterms,
+               "fqeb_taylor: NULL argument");
+  FQEB_REQUIRE(d_evol != d_work && d_evol != d_next && d_work != d_next,
+               "fqeb_taylor: evol / work / next buffers must be distinct");
+  const int64_t n = g->len[0] * g->len[1];
+  cudaStream_t st = (cudaStream_t)stream;
+  FQEB_CUDA(cudaMemcpyAsync(d_work, d_evol, sizeof(double) * 2 * (size_t)n,
+                            cudaMemcpyDeviceToDevice, st));
+  double factorial = 1.0;
+  for (int order = 1; order < max_terms; ++order) {
+    rc = fqeb_sigma_restricted(g, op, d_work, d_next, d_workspace, workspace_bytes, 0, g->len[0],
+                               0, op->np, stream);
+    if (rc != FQEB_OK) return rc;
+    double *t = d_work;
+    d_work = d_next;
+    d_next = t;
+    factorial *= (double)order;
+    const double coeff = 1.0 / factorial;
+    double norm2 = 0.0;
+    rc = fqeb_axpy_norm2(n, coeff, 0.0, d_work, d_evol, d_scratch, &norm2, stream);
+    if (rc != FQEB_OK) return rc;
+    if (sqrt(norm2) * coeff < accuracy) {
+      *nterms = order;
+      return FQEB_OK;
+    }
+  }
+  *nterms = max_terms;
+  set_error("maximum taylor expansion limit reached (%d terms)", max_terms);
+  return FQEB_ERR_CONVERGE;
+}
+
 extern "C" int fqeb_profile_enable(int on) {
   std::lock_guard<std::mutex> lock(g_profile_mu);
   g_profile = on != 0;

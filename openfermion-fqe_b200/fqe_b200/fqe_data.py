@@ -435,6 +435,34 @@ class FqeData:
                   r0, r1, p0, p1, _stream())
         return sigma
 
+    def taylor_inplace(self, op: DenseOperator, accuracy: float = 1.0e-15,
+                       expansion: int = 30) -> int:
+        """coeff <- sum_k op^k coeff / k! with the whole recurrence in one native call
+        (``fqeb_taylor``); ``op`` is prepared from the tensors of -i*t*H.  Returns the number of
+        terms; raises RuntimeError when ``expansion`` is reached (wavefunction.py:548-567)."""
+        dev = _require_cuda()
+        if op.norb != self.norb():
+            raise ValueError("operator / wavefunction orbital mismatch")
+        lib = _lib.load()
+        ws_ptr, ws_bytes = None, 0
+        if op.has_h2:
+            wanted = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, self.lena(),
+                                                        0, op.npair))
+            minimum = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, 1, 0,
+                                                         op.npair))
+            ws = _workspace(dev, wanted, minimum)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+        work, nxt = torch.empty_like(self.coeff), torch.empty_like(self.coeff)
+        nterms = ctypes.c_int()
+        code = lib.fqeb_taylor(self._core.handle, op.handle,
+                               self._check_coeff(self.coeff).data_ptr(), work.data_ptr(),
+                               nxt.data_ptr(), ws_ptr, ws_bytes, _reduce_scratch(dev).data_ptr(),
+                               float(accuracy), int(expansion), ctypes.byref(nterms), _stream())
+        if code == _lib.ERR_CONVERGE:
+            raise RuntimeError("maximum taylor expansion limit reached")
+        _lib.check(code)
+        return int(nterms.value)
+
     def _apply_array_spatial1(self, h1e: numpy.ndarray) -> torch.Tensor:
         assert h1e.shape == (self.norb(), self.norb())
         return self.apply_operator(DenseOperator(self.norb(), h1e, None))

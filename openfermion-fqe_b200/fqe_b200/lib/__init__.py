@@ -75,6 +75,8 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "fqeb_sparse_scale": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, c_double,
                                   c_double, c_void_p, c_void_p]),
+    "fqeb_taylor": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                            c_void_p, c_double, c_int, POINTER(c_int), c_void_p]),
     "fqeb_reduce_scratch_bytes": (c_size_t, []),
     "fqeb_zaxpy": (c_int, [c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "fqeb_zscal": (c_int, [c_int64, c_double, c_double, c_void_p, c_void_p]),

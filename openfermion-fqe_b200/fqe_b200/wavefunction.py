@@ -306,6 +306,14 @@ class Wavefunction:
             ham_arrays = hamil.iht(time)
             op = self._dense_operator(ham_arrays) if len(ham_arrays) <= 2 else None
             time_evol = copy.deepcopy(base)
+            if op is not None and len(self._civec) == 1:
+                # one sector: the whole recurrence runs inside the library (fqeb_taylor)
+                (sec,) = time_evol._civec.values()
+                order = sec.taylor_inplace(op, accuracy, expansion)
+                self.last_expansion_order = order
+                if numpy.abs(hamil.e_0() * time) > 1.e-15:
+                    time_evol.scale(numpy.exp(-1.j * time * hamil.e_0()))
+                return time_evol
             work = copy.deepcopy(base)
             for order in range(1, expansion):
                 work = work._apply_operator(op) if op is not None else \
