@@ -69,10 +69,11 @@ def _reduce_scratch(dev: torch.device) -> torch.Tensor:
     return _SCRATCH[dev]
 
 
-def _workspace(dev: torch.device, wanted: int, minimum: int) -> torch.Tensor:
+def _workspace(dev: torch.device, wanted: int, minimum: int, reserve: int = 0) -> torch.Tensor:
     """A byte workspace of at most ``wanted`` and at least ``minimum`` bytes, bounded by
-    settings.workspace_fraction of the free memory.  Cached (and grown on demand) so
-    that repeated sigma builds - the Taylor loop - never reallocate."""
+    settings.workspace_fraction of the free memory and leaving ``reserve`` bytes (one more
+    coefficient vector) unclaimed.  Cached (and grown on demand) so that repeated sigma
+    builds - the Taylor loop - never reallocate."""
     cur = _WORKSPACE.get(dev)
     if cur is not None and (cur.numel() >= wanted or
                             (dev in _WS_CAPPED and cur.numel() >= minimum)):
@@ -83,7 +84,7 @@ def _workspace(dev: torch.device, wanted: int, minimum: int) -> torch.Tensor:
     del cur
     torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info(dev)
-    budget = int(free * settings.workspace_fraction)
+    budget = min(int(free * settings.workspace_fraction), free - reserve - (1 << 30))
     if settings.max_workspace_bytes is not None:
         budget = min(budget, int(settings.max_workspace_bytes))
     size = min(wanted, max(budget, minimum, have))
@@ -428,7 +429,7 @@ class FqeData:
             wanted = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, r1 - r0,
                                                         p0, p1))
             minimum = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, 1, p0, p1))
-            ws = _workspace(dev, wanted, minimum)
+            ws = _workspace(dev, wanted, minimum, reserve=16 * self._n())
             ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
         _lib.call("fqeb_sigma_restricted", self._core.handle, op.handle,
                   self._check_coeff(self.coeff).data_ptr(), sigma.data_ptr(), ws_ptr, ws_bytes,
@@ -450,7 +451,7 @@ class FqeData:
                                                         0, op.npair))
             minimum = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, 1, 0,
                                                          op.npair))
-            ws = _workspace(dev, wanted, minimum)
+            ws = _workspace(dev, wanted, minimum, reserve=32 * self._n())
             ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
         work, nxt = torch.empty_like(self.coeff), torch.empty_like(self.coeff)
         nterms = ctypes.c_int()
