@@ -325,3 +325,35 @@ def test_host_apply_stream_pipelines_independent_builds():
         d.set_wfn(strategy="from_data", raw_data=c.numpy())
         ref = d.apply_operator(op).cpu().numpy()
         assert O.rel_err(s.numpy(), ref) < 1e-14
+
+
+@pytest.mark.parametrize("cfg", [(0, 0, 3), (1, 0, 1), (0, 1, 1), (2, 2, 2), (0, 0, 1)])
+def test_degenerate_sectors(cfg):
+    """vacuum, single orbital, completely filled: one-determinant sectors through every
+    entry point (no electrons: the absorbed one-body operand cannot be used)"""
+    import fqe_b200
+    from fqe_b200 import synth
+    from fqe_b200.fqe_data import FqeData
+    na, nb, norb = cfg
+    h1, h2 = synth.integrals(norb, "herm", seed=1)
+    g = O.graph(na, nb, norb)
+    c = synth.state(g.lena, g.lenb, seed=2)
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    ref = O.sigma_restricted(g, c, h1, h2)
+    out = d.apply((h1, h2)).to_numpy()
+    assert np.abs(out - ref).max() < 1e-13
+    out = d.apply((h1,)).to_numpy()
+    assert np.abs(out - O.sigma_one_body(g, c, h1)).max() < 1e-13
+    wfn = fqe_b200.Wavefunction([[na + nb, na - nb, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(na + nb, na - nb): c})
+    ham = fqe_b200.get_restricted_hamiltonian((h1, h2), e_0=0.5)
+    ev = wfn.time_evolve(0.05, ham).get_coeff((na + nb, na - nb))
+    refev, _ = O.time_evolve_restricted(g, c, 0.05, h1, h2, 0.5)
+    assert np.abs(ev - refev).max() < 1e-13
+    quad = wfn.time_evolve(0.3, fqe_b200.get_restricted_hamiltonian((h1,)))
+    assert np.abs(quad.get_coeff((na + nb, na - nb)) -
+                  O.time_evolve_quadratic(g, c, 0.3, h1)).max() < 1e-13
+    r1, r2 = d.rdm12()
+    o1, o2 = O.rdm12(g, c)
+    assert np.abs(r1 - o1).max() < 1e-13 and np.abs(r2 - o2).max() < 1e-13
