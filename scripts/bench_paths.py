@@ -66,14 +66,31 @@ rot_ham = fqe.get_restricted_hamiltonian((kmat,))
 dc_ham = fqe.get_diagonalcoulomb_hamiltonian(vij)
 ms = timed(lambda: sec.apply((kmat,)), reps=3, warm=1)
 out["one_body_sigma_norb16"] = {"ms": ms}
+wfn.time_evolve(0.01, rot_ham)          # warm-up: builds the occupancy lists once
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 step = wfn.time_evolve(0.01, rot_ham)
 step = step.time_evolve(0.01, dc_ham, inplace=True)
 torch.cuda.synchronize()
+norm0 = wfn.norm()
 out["trotter_step_norb16"] = {"seconds": time.perf_counter() - t0,
-                              "rotation_taylor_terms": wfn.last_expansion_order,
-                              "norm_after": step.norm()}
+                              "route": "transform -> evolve_diagonal -> transform, then DC evolve",
+                              "norm_ratio_after": step.norm() / norm0}
+# one orbital rotation alone (Wavefunction.transform: 2*norb column passes), in place
+from scipy.linalg import expm
+umat = expm(-0.3j * kmat)
+rot = wfn.time_evolve(0.0, dc_ham)      # a copy to rotate
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+rot.transform(umat)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+# algorithmic bytes per rotation: 2*norb columns x 16*L^2*(n/2 + 2)
+rbytes = 2 * norb * 16.0 * la * lb * (na / 2 + 2)
+out["transform_norb16"] = {"seconds": dt, "algorithmic_GBps": rbytes / dt / 1e9,
+                           "frac_hbm": rbytes / dt / 1e9 / HBM,
+                           "norm_ratio_after": rot.norm() / norm0}
+del rot
 del wfn, sec, other, step
 torch.cuda.empty_cache()
 
@@ -102,4 +119,45 @@ dt = time.perf_counter() - t0
 out["time_evolve_norb14"] = {"t": t, "H_norm_est": hn, "taylor_terms": wfn.last_expansion_order
                              if hasattr(wfn, "last_expansion_order") else None,
                              "seconds": dt, "norm_after": ev.norm()}
+del wfn, ev, x, y
+torch.cuda.empty_cache()
+
+# ---- config 5: sweep of individual 3-body operators at norb=12, n=12 -----------------------
+norb, n, sz = 12, 12, 0
+na, nb, la, lb = synth.sector_dims(n, sz, norb)
+wfn = fqe.Wavefunction([[n, sz, norb]])
+wfn.set_wfn(strategy="from_data", raw_data={(n, sz): synth.state(la, lb, seed=12)})
+sec = wfn.sector((n, sz))
+rng = np.random.default_rng(5)
+terms = []
+for _ in range(200):
+    ka = int(rng.integers(0, 4))                     # alpha operators of the 3-body term
+    daga = sorted(rng.choice(norb, ka, replace=False).tolist(), reverse=True)
+    unda = sorted(rng.choice(norb, ka, replace=False).tolist(), reverse=True)
+    dagb = sorted(rng.choice(norb, 3 - ka, replace=False).tolist(), reverse=True)
+    undb = sorted(rng.choice(norb, 3 - ka, replace=False).tolist(), reverse=True)
+    terms.append((complex(rng.standard_normal(), rng.standard_normal()), daga, unda, dagb, undb))
+acc = sec.empty_copy(zero=True)
+
+
+def sweep():
+    for c, da, ua, db, ub in terms:
+        acc.apply_individual_nbody_accumulate(c, sec, da, ua, db, ub)
+
+
+ms = timed(sweep, reps=3, warm=1)
+out["individual_3body_sweep_norb12"] = {"terms": len(terms), "ms_per_term": ms / len(terms)}
+ev_terms = [t for t in terms if not (t[1] == t[2] and t[3] == t[4])][:50]
+
+
+def evolve_sweep():
+    cur = sec
+    for c, da, ua, db, ub in ev_terms:
+        cur = cur.evolve_individual_nbody_nontrivial(0.1, c, da, ua, db, ub)
+    return cur
+
+
+ms = timed(evolve_sweep, reps=2, warm=1)
+out["individual_3body_evolve_norb12"] = {"terms": len(ev_terms), "ms_per_term": ms / len(ev_terms),
+                                         "norm_after": evolve_sweep().norm()}
 print(json.dumps(out))
