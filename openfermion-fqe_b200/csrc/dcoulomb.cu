@@ -64,8 +64,11 @@ __global__ void k_dc_string_terms(int norb, int64_t len, const uint64_t *__restr
 // evaluated with byte-indexed lookup tables built once per row in shared memory
 // (tab[k][m] = combination of cross_a[8k + bit] over the bits of m), so an element costs
 // ceil(norb/8) shared-memory lookups instead of a loop over its nbeta set bits.
+#ifndef FQEB_DC_MINB
+#define FQEB_DC_MINB 4
+#endif
 template <bool EVOLVE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FQEB_DC_MINB)
 k_dc_main(int norb, int64_t lena, int64_t lenb, const uint64_t *__restrict__ astr,
           const uint64_t *__restrict__ bstr, const double2 *__restrict__ v,
           const double2 *__restrict__ aterm, const double2 *__restrict__ bterm,
@@ -111,7 +114,10 @@ k_dc_main(int norb, int64_t lena, int64_t lenb, const uint64_t *__restrict__ ast
     const double2 at = aterm[a];
     double2 *__restrict__ row = coeff + a * lenb;
     // four elements per trip: all loads first (memory-level parallelism), then math + stores
-    constexpr int U = 4;
+#ifndef FQEB_DC_U
+#define FQEB_DC_U 4
+#endif
+    constexpr int U = FQEB_DC_U;
     for (int64_t b0 = threadIdx.x; b0 < lenb; b0 += (int64_t)U * blockDim.x) {
       uint64_t sb[U];
       double2 bt[U], cv[U];
@@ -121,7 +127,11 @@ k_dc_main(int norb, int64_t lena, int64_t lenb, const uint64_t *__restrict__ ast
         const bool on = b < lenb;
         sb[u] = on ? __ldg(bstr + b) : 0ull;
         bt[u] = on ? __ldg(bterm + b) : ident;
+#ifdef FQEB_DC_STREAM
+        cv[u] = on ? __ldcs(row + b) : make_double2(0.0, 0.0);
+#else
         cv[u] = on ? row[b] : make_double2(0.0, 0.0);
+#endif
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -139,7 +149,11 @@ k_dc_main(int norb, int64_t lena, int64_t lenb, const uint64_t *__restrict__ ast
         } else {
           f = zadd(zadd(x, bt[u]), at);
         }
+#ifdef FQEB_DC_STREAM
+        if (b < lenb) __stcs(row + b, zmul(cv[u], f));
+#else
         if (b < lenb) row[b] = zmul(cv[u], f);
+#endif
       }
     }
     __syncthreads();
@@ -179,9 +193,16 @@ static int dc_run(const fqeb_graph *g, const double *h_diag, const double *h_arr
   }
   const double2 *aterm = (const double2 *)g->d_sterm[0];
   const double2 *bterm = (const double2 *)g->d_sterm[g->shared_spin ? 0 : 1];
-  int64_t grid = (int64_t)sm_count() * 8;
-  if (grid > g->len[0]) grid = g->len[0];
   const size_t tab_bytes = sizeof(double2) * 256 * (size_t)((norb + 7) / 8);
+  // persistent grid: exactly the CTAs that are resident at once, so that every CTA walks the
+  // same number of rows (8 CTAs per SM with only 3 resident left a 2/3-empty last wave)
+  int per_sm = 0;
+  FQEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_main<EVOLVE>, 256,
+                                                          tab_bytes));
+  if (getenv("FQEB_DC_CTAS_PER_SM")) per_sm = atoi(getenv("FQEB_DC_CTAS_PER_SM"));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > g->len[0]) grid = g->len[0];
   k_dc_main<EVOLVE><<<(unsigned)grid, 256, tab_bytes, st>>>(norb, g->len[0], g->len[1], g->d_str[0],
                                                     g->d_str[1], use_v, aterm, bterm,
                                                     (double2 *)d_coeff);
