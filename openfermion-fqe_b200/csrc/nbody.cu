@@ -10,8 +10,8 @@
 // An individual operator is  z * prod a^+_{dag} prod a_{undag}  on the alpha strings times the
 // same on the beta strings.  Each spin part is a signed partial permutation of the string
 // space.  The reference materialises it as a (source, target, parity) list on the host; here
-// one kernel per spin writes its INVERSE as a by-target table inv[t] = sign * (s + 1) (0: no
-// source), so that the accumulation
+// one kernel writes the INVERSE of both spin parts as by-target tables inv[t] = sign * (s + 1)
+// (0: no source), so that the accumulation
 //       out[ta, tb] += z * pa * pb * in[sa, sb]
 // is a coalesced by-target gather over the (few) target rows: no host round trip, no atomics.
 //
@@ -32,30 +32,44 @@ __device__ __forceinline__ int bits_above(uint64_t s, int i) {
   return __popcll(s >> (i + 1));
 }
 
-// inv[target] = sign * (source + 1) for every string the operator does not annihilate
-__global__ void k_nbody_invmap(int norb, int64_t len, const uint64_t *__restrict__ str,
-                               const int32_t *__restrict__ z, OpList ops,
-                               int32_t *__restrict__ inv) {
+// By-target table of both spin parts in one launch (blockIdx.y = spin):
+//   inv[t] = sign * (s + 1)  with  A |s> = sign |t>,   0 if no string maps onto t.
+// The source of a target is found by walking the ADJOINT operator
+//   A^+ = a^+_{u_k} ... a^+_{u_1} a_{d_k} ... a_{d_1}      (A = a^+_{d_1}..a^+_{d_k} a_{u_1}..a_{u_k})
+// on t, rightmost operator first; the sign of <t|A|s> equals the sign of <s|A^+|t>, and each
+// step's sign is (-1)^(occupied orbitals above the one acted on), as in the reference's
+// make_mapping_each (lib/fci_graph.c:248-257).  Every entry is written, so no memset is needed.
+__global__ void k_nbody_invmap(int norb, int64_t lena, int64_t lenb,
+                               const uint64_t *__restrict__ astr, const uint64_t *__restrict__ bstr,
+                               const int32_t *__restrict__ za, const int32_t *__restrict__ zb,
+                               OpList opa, OpList opb, int32_t *__restrict__ inva,
+                               int32_t *__restrict__ invb) {
+  const bool beta = blockIdx.y != 0;
+  const int64_t len = beta ? lenb : lena;
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= len) return;
-  uint64_t cur = str[x];
+  const OpList &ops = beta ? opb : opa;
+  uint64_t cur = (beta ? bstr : astr)[x];
   int parity = 0;
-  // rightmost operator first (lib/fci_graph.c:248-257); an annihilator on an empty or a
-  // creator on an occupied orbital kills the string
-  for (int j = ops.nundag - 1; j >= 0; --j) {
-    const int o = ops.undag[j];
-    if (!((cur >> o) & 1ull)) return;
+  bool ok = true;
+  for (int j = 0; j < ops.ndag && ok; ++j) {      // a_{d_1} first
+    const int o = ops.dag[j];
+    ok = (cur >> o) & 1ull;
     parity += bits_above(cur, o);
     cur &= ~(1ull << o);
   }
-  for (int j = ops.ndag - 1; j >= 0; --j) {
-    const int o = ops.dag[j];
-    if ((cur >> o) & 1ull) return;
+  for (int j = 0; j < ops.nundag && ok; ++j) {    // then a^+_{u_1}
+    const int o = ops.undag[j];
+    ok = !((cur >> o) & 1ull);
     parity += bits_above(cur, o);
     cur |= (1ull << o);
   }
-  const int t = fqeb_string_address(cur, z, norb);
-  inv[t] = (parity & 1) ? -(int32_t)(x + 1) : (int32_t)(x + 1);
+  int32_t val = 0;
+  if (ok) {
+    const int s = fqeb_string_address(cur, beta ? zb : za, norb);
+    val = (parity & 1) ? -(int32_t)(s + 1) : (int32_t)(s + 1);
+  }
+  (beta ? invb : inva)[x] = val;
 }
 
 __global__ void __launch_bounds__(kNB)
@@ -129,13 +143,9 @@ extern "C" int fqeb_nbody_accumulate(const fqeb_graph *g, double zr, double zi, 
   cudaStream_t st = (cudaStream_t)stream;
   // by-target tables live in the per-string scratch of the graph (16 bytes per string)
   int32_t *inva = (int32_t *)g->d_sterm[0], *invb = (int32_t *)g->d_sterm[1];
-  FQEB_CUDA(cudaMemsetAsync(inva, 0, sizeof(int32_t) * (size_t)lena, st));
-  FQEB_CUDA(cudaMemsetAsync(invb, 0, sizeof(int32_t) * (size_t)lenb, st));
-  k_nbody_invmap<<<(unsigned)((lena + kNB - 1) / kNB), kNB, 0, st>>>(g->norb, lena, g->d_str[0],
-                                                                    g->d_Z[0], oa, inva);
-  FQEB_CHECK_LAUNCH();
-  k_nbody_invmap<<<(unsigned)((lenb + kNB - 1) / kNB), kNB, 0, st>>>(g->norb, lenb, g->d_str[1],
-                                                                    g->d_Z[1], ob, invb);
+  const int64_t lmax = lena > lenb ? lena : lenb;
+  k_nbody_invmap<<<dim3((unsigned)((lmax + kNB - 1) / kNB), 2), kNB, 0, st>>>(
+      g->norb, lena, lenb, g->d_str[0], g->d_str[1], g->d_Z[0], g->d_Z[1], oa, ob, inva, invb);
   FQEB_CHECK_LAUNCH();
   const int nbt = (int)((lenb + kNB - 1) / kNB);
   FQEB_REQUIRE(lena * nbt < (1ll << 31), "fqeb_nbody_accumulate: problem too large");
