@@ -93,6 +93,11 @@ __device__ __forceinline__ double2 ldg_c128_if_g(bool pred, const double2 *p) {
   return v;
 }
 
+// exact sign flip: XOR the sign bit of the map entry into the double
+__device__ __forceinline__ double flip_sign_g(double v, int t) {
+  return __hiloint2double(__double2hiint(v) ^ (t & (int)0x80000000), __double2loint(v));
+}
+
 // ---- fragment loads with compile-time offsets ------------------------------------------
 // Written as asm with an immediate offset from ONE base register per operand: left to
 // itself the compiler, short of registers next to 136 accumulator registers,
@@ -729,44 +734,46 @@ static GemmShape pick_shape(bool cplx, int m_valid) {
 }
 
 // ---- fused gather + contraction ----------------------------------------------------------
-// The D tensor is never written to HBM: four PRODUCER warps build each 16-pair x 64-
-// determinant tile of D directly in the shared-memory ring (signed gathers from C,
-// exactly what k_make_dvec computes) while the eight CONSUMER warps run the DMMA
-// stream on the previous tiles.  Applies when one CTA covers all rows of the operator
-// (pair space <= 144, real/imaginary class: norb=16 with real-orbital integrals) so that
-// no D tile is gathered twice.  The one-body term is folded into the operand beforehand
-// (h2'[ij,kk] += h1'[ij]/n_elec, exact on a fixed-particle-number sector), so sigma gets
-// everything through E.  Saves writing and re-reading D (2 x 360 GB per sigma at
-// norb=16) and the whole gather launch.
+// The D tensor is never written to HBM: two PRODUCER warpgroups (256 threads) build each
+// 32-pair x 64-determinant tile of D directly in the shared-memory ring, as signed
+// single-source gathers from C (exactly what k_gather computes, from the plain or the merged
+// pair-space map), and stream the operand tile next to it with cp.async, while the two
+// CONSUMER warpgroups run the DMMA stream of k_dgemm_ws on the previous stages.  setmaxnreg
+// splits the register file 80 / 176 between the two roles.  Applies when one CTA covers all
+// rows of the operator (pair space <= 144, real / imaginary class: norb=16 with real-orbital
+// integrals), so that no D tile is gathered twice.  The one-body term is folded into the
+// operand beforehand (absorbed_operand), so sigma gets everything through E.  Saves writing
+// and re-reading D (2 x 360 GB per sigma at norb=16) and the whole gather launch.
 //
 // Column space: determinants of a chunk are laid out with a row pitch that is a multiple
 // of 64, so a tile never straddles two alpha rows:  col = r*pitch + b.
+// Producer thread p: determinant p & 63 of the tile, pair rows (p >> 6) + 4*j of every stage.
 template <int WM, bool RAGGED>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, int k_valid,
-              const int32_t *__restrict__ pairs, const int32_t *__restrict__ amapT_a,
-              const int32_t *__restrict__ amap_b, int npair_total,
+              const int32_t *__restrict__ mapT_a, const int32_t *__restrict__ map_b, int ntab,
               const double2 *__restrict__ coeff, int64_t lenb, int64_t row0, int pitch,
               int tiles_per_row, double2 *__restrict__ E, int64_t lde, int m_valid,
               int nrows_out, int64_t ntiles) {
-  constexpr int WN = 2;
+  constexpr int KS = 32, NST = 3, WN = 2;
   constexpr int BM = WM * 8;
+  constexpr int A_STRIDE = KS + 4;
   constexpr int A_TILE = BM * A_STRIDE;
-  constexpr int STAGE_DOUBLES = A_TILE + B_TILE;
-  constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  constexpr int B_TILE = KS * B_STRIDE_R;
+  constexpr int STAGE_BYTES = (A_TILE + B_TILE) * 8;
   constexpr int TILE_DETS = BNR / 2;  // 64
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int nk = (k_valid + KSTEP - 1) / KSTEP;
+  const int nk = (k_valid + KS - 1) / KS;
   const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned bar_full = smem_u32 + STAGES * STAGE_BYTES;
-  const unsigned bar_empty = bar_full + STAGES * 8;
+  const unsigned bar_full = smem_u32 + NST * STAGE_BYTES;
+  const unsigned bar_empty = bar_full + NST * 8;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + s * 8, 64);   // one producer warp: 32 lanes x (cp.async arrive + arrive)
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_full + s * 8, 512);  // 256 producer threads x (cp.async arrive + arrive)
       mbar_init(bar_empty + s * 8, 8);   // one arrive per consumer warp
     }
   }
@@ -776,126 +783,120 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
   int64_t nb = blockIdx.x;
 
   if (warp >= 8) {
-    // =========================== producers ===========================================
-    // Stage-parallel: producer warp w fills ring slots w, w+4, ... on its own (operand
-    // tile by cp.async, D tile by signed gathers), so each warp has STAGES consumer
-    // stage-times to hide its global-load latency.  Lane l owns determinants l and l+32
-    // of the 64-determinant tile and walks the 16 pair rows of the stage in batches of
-    // two rows; the map lookups of batch q+1 are issued before batch q is combined.
-    const int pw = warp - 8;           // 0..3 == ring slot owned
-    const unsigned a_dst0 = smem_u32 + ((lane >> 3) * A_STRIDE + (lane & 7) * 2) * 8;
-    const double *a_src0 = A + a_col0 + (int64_t)(lane >> 3) * lda + (lane & 7) * 2;
-    const unsigned b_dst0 = smem_u32 + (A_TILE + 2 * lane) * 8;
-    const unsigned sbase = pw * STAGE_BYTES;
-    const unsigned full_bar = bar_full + pw * 8, empty_bar = bar_empty + pw * 8;
+    // =========================== producers (warpgroups 2, 3) =========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;\n");
+    const int pt = tid - 256;
+    const int det = pt & 63, phase = pt >> 6;
+    int stage = 0;
     unsigned round_parity = 1;
     bool first_round = true;
-    const int64_t total_it = my_tiles * nk;
-    // position of this warp's first stage
-    int64_t t = pw / nk;
-    int kt = pw % nk;
-    nb += t * gridDim.x;
-    for (int64_t it = pw; it < total_it; it += STAGES) {
-      const int r = (int)(nb / tiles_per_row);
-      const int bt = (int)(nb - (int64_t)r * tiles_per_row);
+    // Software pipeline over "trips" (4 pair rows of one determinant): the map entries of
+    // trip n+1 are requested before the C elements of trip n are consumed, across stage and
+    // tile boundaries, so a trip costs one global round trip instead of two dependent ones.
+    struct Coords {
+      const int32_t *ta_row, *mb;
+      const double2 *crow, *ccol;
+      bool valid;
+    };
+    auto tile_coords = [&](int64_t tile) {
+      Coords c;
+      const int r = (int)(tile / tiles_per_row);
+      const int bt = (int)(tile - (int64_t)r * tiles_per_row);
       const int64_t a = row0 + r;
-      const int64_t b0 = (int64_t)bt * TILE_DETS + lane;
-      const int64_t b1 = b0 + 32;
-      const bool v0 = b0 < lenb, v1 = b1 < lenb;
-      const int32_t *__restrict__ ta_row = amapT_a + a * (int64_t)npair_total;
-      const double2 *__restrict__ crow = coeff + a * lenb;
-      const double2 *__restrict__ ccol0 = coeff + (v0 ? b0 : 0);
-      const double2 *__restrict__ ccol1 = coeff + (v1 ? b1 : 0);
-      const int32_t *__restrict__ mb0 = amap_b + (v0 ? b0 : 0);
-      const int32_t *__restrict__ mb1 = amap_b + (v1 ? b1 : 0);
-
-      if (!first_round) mbar_wait(empty_bar, round_parity);
-      // operand tile: BM rows x 8 chunks, 4 rows per pass of the warp
-      {
-        const double *a_src = a_src0 + kt * KSTEP;
-#pragma unroll 6
-        for (int i = 0; i < BM / 4; ++i)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                           a_dst0 + sbase + i * 4 * A_STRIDE * 8),
-                       "l"(a_src + (int64_t)(i * 4) * lda));
-        cp_async_mbar_arrive(full_bar);
+      const int64_t bb = (int64_t)bt * TILE_DETS + det;
+      c.valid = bb < lenb;
+      c.ta_row = mapT_a + a * (int64_t)ntab + c_first;
+      c.crow = coeff + a * lenb;
+      c.ccol = coeff + (c.valid ? bb : 0);
+      c.mb = map_b + (int64_t)c_first * lenb + (c.valid ? bb : 0);
+      return c;
+    };
+    auto load_maps = [&](const Coords &c, int kbase, int (&ta_)[4], int (&tb_)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kbase + 4 * u;
+        const bool on = k < k_valid;
+        ta_[u] = on ? ldg_int_g(c.ta_row + k) : 0;
+        tb_[u] = (on && c.valid) ? ldg_int_g(c.mb + (int64_t)k * lenb) : 0;
       }
-      // D tile.  batch q = pair rows (2q, 2q+1) of the stage for both determinants.
-      // lookups of one batch: ij (2 rows x 2 pairs), ta (4), tb (4 per determinant)
-      int ij[4], ta[4], tb0[4], tb1[4];
-      auto lookups = [&](int q, int (&ij_)[4], int (&ta_)[4], int (&t0_)[4], int (&t1_)[4]) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = kt * KSTEP + 2 * q + h;
-          const bool on = c < k_valid;
-          ij_[2 * h] = on ? ldg_int_g(pairs + 2 * (c_first + c)) : -1;
-          ij_[2 * h + 1] = on ? ldg_int_g(pairs + 2 * (c_first + c) + 1) : -1;
+    };
+    Coords cur = tile_coords(nb);
+    int ta[4], tb[4];
+    load_maps(cur, phase, ta, tb);
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      for (int kt = 0; kt < nk; ++kt) {
+        if (!first_round) mbar_wait(bar_empty + stage * 8, round_parity);
+        const unsigned sbase = smem_u32 + stage * STAGE_BYTES;
+        // operand tile: BM rows x 16 chunks of 16 bytes, spread over the 256 producer threads
+        {
+          const double *a_src = A + a_col0 + kt * KS;
+#pragma unroll 3
+          for (int q = pt; q < BM * (KS / 2); q += 256) {
+            const int row = q >> 4, cc = q & 15;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                             sbase + (row * A_STRIDE + cc * 2) * 8),
+                         "l"(a_src + (int64_t)row * lda + cc * 2));
+          }
+          cp_async_mbar_arrive(bar_full + stage * 8);
         }
+        // D tile: this thread's 8 pair rows of the stage, two trips of four
+        const unsigned d_dst = sbase + (A_TILE + phase * B_STRIDE_R + 2 * det) * 8;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const bool on = ij_[h] >= 0;
-          ta_[h] = on ? ldg_int_g(ta_row + ij_[h]) : 0;
-          t0_[h] = (on && v0) ? ldg_int_g(mb0 + (int64_t)ij_[h] * lenb) : 0;
-          t1_[h] = (on && v1) ? ldg_int_g(mb1 + (int64_t)ij_[h] * lenb) : 0;
+        for (int trip = 0; trip < 2; ++trip) {
+          double2 va[4], vb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            va[u] = ldg_c128_if_g(ta[u] != 0 && cur.valid,
+                                  cur.ccol + (int64_t)(abs(ta[u]) - 1) * lenb);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            vb[u] = ldg_c128_if_g(tb[u] != 0, cur.crow + (abs(tb[u]) - 1));
+          // maps of the next trip: second half of this stage, or the first half of the next
+          // stage (possibly of the next tile)
+          int nta[4], ntb[4];
+          Coords nxt = cur;
+          if (trip == 0) {
+            load_maps(cur, kt * KS + phase + 16, nta, ntb);
+          } else if (kt + 1 < nk) {
+            load_maps(cur, (kt + 1) * KS + phase, nta, ntb);
+          } else if (t + 1 < my_tiles) {
+            nxt = tile_coords(nb + gridDim.x);
+            load_maps(nxt, phase, nta, ntb);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nta[u] = ntb[u] = 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double re = flip_sign_g(va[u].x, ta[u]) + flip_sign_g(vb[u].x, tb[u]);
+            const double im = flip_sign_g(va[u].y, ta[u]) + flip_sign_g(vb[u].y, tb[u]);
+            asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(
+                             d_dst + (4 * (4 * trip + u)) * B_STRIDE_R * 8),
+                         "d"(re), "d"(im)
+                         : "memory");
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ta[u] = nta[u];
+            tb[u] = ntb[u];
+          }
+          cur = nxt;
         }
-      };
-      lookups(0, ij, ta, tb0, tb1);
-#pragma unroll 1
-      for (int q = 0; q < KSTEP / 2; ++q) {
-        // C elements of batch q: alpha sources (shared by both determinants' columns)
-        double2 va0[4], va1[4], vb0[4], vb1[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int64_t arow = (int64_t)(abs(ta[h]) - 1) * lenb;
-          va0[h] = ldg_c128_if_g(ta[h] != 0 && v0, ccol0 + arow);
-          va1[h] = ldg_c128_if_g(ta[h] != 0 && v1, ccol1 + arow);
-          vb0[h] = ldg_c128_if_g(tb0[h] != 0, crow + (abs(tb0[h]) - 1));
-          vb1[h] = ldg_c128_if_g(tb1[h] != 0, crow + (abs(tb1[h]) - 1));
-        }
-        // lookups of the next batch go out before this one is consumed
-        int nij[4], nta[4], nt0[4], nt1[4];
-        if (q + 1 < KSTEP / 2) lookups(q + 1, nij, nta, nt0, nt1);
-        auto sgn = [](int x) { return x < 0 ? -1.0 : 1.0; };
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k0 = 2 * h, k1 = 2 * h + 1;  // the (up to) two pairs of this row
-          const double re0 = (sgn(ta[k0]) * va0[k0].x + sgn(tb0[k0]) * vb0[k0].x) +
-                             (sgn(ta[k1]) * va0[k1].x + sgn(tb0[k1]) * vb0[k1].x);
-          const double im0 = (sgn(ta[k0]) * va0[k0].y + sgn(tb0[k0]) * vb0[k0].y) +
-                             (sgn(ta[k1]) * va0[k1].y + sgn(tb0[k1]) * vb0[k1].y);
-          const double re1 = (sgn(ta[k0]) * va1[k0].x + sgn(tb1[k0]) * vb1[k0].x) +
-                             (sgn(ta[k1]) * va1[k1].x + sgn(tb1[k1]) * vb1[k1].x);
-          const double im1 = (sgn(ta[k0]) * va1[k0].y + sgn(tb1[k0]) * vb1[k0].y) +
-                             (sgn(ta[k1]) * va1[k1].y + sgn(tb1[k1]) * vb1[k1].y);
-          const unsigned dst = b_dst0 + sbase + (2 * q + h) * B_STRIDE_R * 8;
-          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst), "d"(re0), "d"(im0)
-                       : "memory");
-          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst + 64 * 8), "d"(re1), "d"(im1)
-                       : "memory");
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          ij[h] = nij[h];
-          ta[h] = nta[h];
-          tb0[h] = nt0[h];
-          tb1[h] = nt1[h];
+        mbar_arrive(bar_full + stage * 8);
+        if (++stage == NST) {
+          stage = 0;
+          round_parity ^= 1;
+          first_round = false;
         }
       }
-      mbar_arrive(full_bar);
-      round_parity ^= 1;
-      first_round = false;
-      // advance this warp by STAGES stages
-      kt += STAGES;
-      while (kt >= nk) {
-        kt -= nk;
-        nb += gridDim.x;
-      }
+      nb += gridDim.x;
     }
     asm volatile("cp.async.wait_all;\n" ::);
     return;
   }
 
-  // ============================= consumers =============================================
+  // ============================= consumers (warpgroups 0, 1) ===========================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n");
   const int g = lane >> 2, tg = lane & 3;
   const int wn0 = warp * (WN * 8);
   const unsigned a_frag_off = (g * A_STRIDE + tg) * 8;
@@ -913,13 +914,13 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
     for (int kt = 0; kt < nk; ++kt) {
       mbar_wait(bar_full + stage * 8, parity);
       const unsigned stage_u32 = smem_u32 + stage * STAGE_BYTES;
-      int kk_count = (k_valid - kt * KSTEP + 3) / 4;
-      kk_count = kk_count > KSTEP / 4 ? KSTEP / 4 : kk_count;
-      mma_stage<false, WM, WN, RAGGED>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off,
-                                       kk_count, mt_active);
+      int kk_count = (k_valid - kt * KS + 3) / 4;
+      kk_count = kk_count > KS / 4 ? KS / 4 : kk_count;
+      mma_stage<false, WM, WN, RAGGED, KS>(acc, stage_u32 + a_frag_off, stage_u32 + b_frag_off,
+                                           kk_count, mt_active);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + stage * 8);
-      if (++stage == STAGES) {
+      if (++stage == NST) {
         stage = 0;
         parity ^= 1;
       }
@@ -933,7 +934,7 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
           double2 *erow = E + (int64_t)kl * lde + n0 + (wn0 >> 1) + tg;
 #pragma unroll
           for (int nt = 0; nt < WN; ++nt)
-            __stcs(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+            store_e(erow + nt * 4, make_double2(acc[mt][nt][0], acc[mt][nt][1]));
         }
       }
     }
@@ -950,7 +951,7 @@ static int launch_fused_wm(const double *d_A, int lda, int a_col0, int c_first, 
                            int64_t row0, int64_t nrows, int pitch, double *d_evec, int64_t lde,
                            int m_valid, cudaStream_t st) {
   constexpr int BM = WM * 8;
-  const size_t smem = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES + 16 * STAGES;
+  const size_t smem = sizeof(double) * (size_t)(BM * (32 + 4) + 32 * B_STRIDE_R) * 3 + 16 * 3;
   const bool ragged = m_valid < BM;
   auto kern = ragged ? k_sigma_fused<WM, true> : k_sigma_fused<WM, false>;
   static bool attr_set = false;
@@ -966,10 +967,10 @@ static int launch_fused_wm(const double *d_A, int lda, int a_col0, int c_first, 
   const int64_t tiles = nrows * tiles_per_row;
   int64_t grid = sm_count();
   if (grid > tiles) grid = tiles;
-  kern<<<(unsigned)grid, 384, smem, st>>>(
-      d_A, lda, a_col0, c_first, k_valid, op->d_pairs, g->d_amapT[0], g->d_amap[1],
-      g->norb * g->norb, (const double2 *)d_coeff, g->len[1], row0, pitch, tiles_per_row,
-      (double2 *)d_evec, lde, m_valid, op->np, tiles);
+  kern<<<(unsigned)grid, 512, smem, st>>>(
+      d_A, lda, a_col0, c_first, k_valid, op->sym ? g->d_smapT[0] : g->d_amapT[0],
+      op->sym ? g->d_smap[1] : g->d_amap[1], op->np, (const double2 *)d_coeff, g->len[1], row0,
+      pitch, tiles_per_row, (double2 *)d_evec, lde, m_valid, op->np, tiles);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }
