@@ -413,10 +413,11 @@ def run_b200(args):
     # same workload (profiles/r01_traffic.json); only quoted for the configuration it was
     # taken on (norb=16, real pair-symmetric operator, one GPU)
     traffic = None
+    fused = main["phase_launches"][0] == 0 and main["phase_launches"][1] > 0
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         if args.norb == 16 and world == 1 and main["op_sym"] and main["op_kind"] != L.OP_COMPLEX:
-            traffic = tr["dram_bytes_per_launch"]
+            traffic = tr["fused"]["dram_bytes_per_launch"] if fused else tr["dram_bytes_per_launch"]
     except Exception:
         pass
     line = {
@@ -448,7 +449,10 @@ def run_b200(args):
                                "synchronize per build, nothing overlapped)",
                 "stream_verify_rel_err": main.get("e2e_stream_verify")},
         "roofline": {
-            "bound": "tensor", "kernel": "k_dgemm (FP64 DMMA contraction)",
+            "bound": "tensor",
+            "kernel": ("k_sigma_fused (D tiles gathered into the shared-memory ring + FP64 DMMA "
+                       "contraction; the gather phase is inside this kernel)") if fused else
+                      "k_dgemm_ws (FP64 DMMA contraction)",
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
             "traffic_unit": "DRAM bytes per contraction launch (ncu), see profiles/r01_traffic.json",

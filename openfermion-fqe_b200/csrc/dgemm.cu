@@ -784,7 +784,22 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
 
   if (warp >= 8) {
     // =========================== producers (warpgroups 2, 3) =========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;\n");
+// diagnostics: compile the alpha / beta source loads out to see what bounds the kernel
+#ifndef FQEB_FUSED_DIAG_A
+#define FQEB_FUSED_DIAG_A true
+#endif
+#ifndef FQEB_FUSED_DIAG_B
+#define FQEB_FUSED_DIAG_B true
+#endif
+#ifndef FQEB_FUSED_PREG
+#define FQEB_FUSED_PREG 80
+#endif
+#ifndef FQEB_FUSED_CREG
+#define FQEB_FUSED_CREG 176   /* 256 - FQEB_FUSED_PREG */
+#endif
+#define FQEB_STR2(x) #x
+#define FQEB_STR(x) FQEB_STR2(x)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " FQEB_STR(FQEB_FUSED_PREG) ";\n");
     const int pt = tid - 256;
     const int det = pt & 63, phase = pt >> 6;
     int stage = 0;
@@ -846,11 +861,11 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
           double2 va[4], vb[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            va[u] = ldg_c128_if_g(ta[u] != 0 && cur.valid,
+            va[u] = ldg_c128_if_g(FQEB_FUSED_DIAG_A && ta[u] != 0 && cur.valid,
                                   cur.ccol + (int64_t)(abs(ta[u]) - 1) * lenb);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            vb[u] = ldg_c128_if_g(tb[u] != 0, cur.crow + (abs(tb[u]) - 1));
+            vb[u] = ldg_c128_if_g(FQEB_FUSED_DIAG_B && tb[u] != 0, cur.crow + (abs(tb[u]) - 1));
           // maps of the next trip: second half of this stage, or the first half of the next
           // stage (possibly of the next tile)
           int nta[4], ntb[4];
@@ -896,7 +911,7 @@ k_sigma_fused(const double *__restrict__ A, int lda, int a_col0, int c_first, in
   }
 
   // ============================= consumers (warpgroups 0, 1) ===========================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 " FQEB_STR(FQEB_FUSED_CREG) ";\n");
   const int g = lane >> 2, tg = lane & 3;
   const int wn0 = warp * (WN * 8);
   const unsigned a_frag_off = (g * A_STRIDE + tg) * 8;

@@ -7,6 +7,8 @@
 //     D[ij]  = E_ij C                      gather        (dvec.cu,  HBM-bound)
 //     E[kl]  = sum_ij h2'[kl,ij] D[ij]     DMMA GEMM     (dgemm.cu, FP64-bound)
 //     sigma += sum_kl E_kl^T E[kl]         scatter       (dvec.cu,  HBM-bound)
+// with the first two steps fused into one kernel where the operator allows it (D tiles are
+// gathered straight into the GEMM's shared-memory ring and never reach HBM).
 //
 // The one-body term sum_ij h1'[ij] D[ij] costs nothing: on a sector with n_elec electrons
 // sum_k D[kk] = n_elec C, so h1'[kl]/n_elec is added to the operand's diagonal-pair columns
@@ -86,13 +88,13 @@ struct ChunkLayout {
   size_t d_bytes, e_bytes;
 };
 
-// The fused gather+contraction kernel (D never written to HBM) is OPT-IN: set
-// FQEB_FUSION=1.  It is parity-tested, but on B200 its four register-staged producer
-// warps cannot keep enough loads in flight per SM (measured at norb=16: 716 ms fused vs
-// 145 ms gather + 395 ms contraction), so the three-kernel path is the default.
+// The fused gather+contraction kernel (D never written to HBM, dgemm.cu k_sigma_fused) is the
+// default wherever it applies: one row block (pair space <= 144), real / imaginary operator
+// class, absorbable one-body term, at least one electron.  Measured at norb=16: 393 ms fused
+// against 79 ms gather + 365 ms contraction.  FQEB_FUSION=0 selects the three-kernel path.
 static bool use_fused(const fqeb_graph *g, const fqeb_op *op) {
   const char *env = getenv("FQEB_FUSION");
-  const bool enabled = env && env[0] == '1';
+  const bool enabled = !(env && env[0] == '0');
   return enabled && op->fuse_ok && (g->nele[0] + g->nele[1]) > 0;
 }
 
