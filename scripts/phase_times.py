@@ -8,7 +8,7 @@ import fqe_b200 as fqe
 from fqe_b200 import lib as L, synth
 from fqe_b200.fqe_data import DenseOperator
 
-norb = 16
+norb = int(sys.argv[sys.argv.index("--norb") + 1]) if "--norb" in sys.argv else 16
 na, nb, la, lb = synth.sector_dims(norb, 0, norb)
 h1, h2 = synth.integrals(norb, "real8")
 wfn = fqe.Wavefunction([[norb, 0, norb]])
