@@ -58,6 +58,36 @@ def build_hamiltonian(ops, norb: int = 0, e_0: complex = 0.0 + 0.0j) -> hamilton
         type(ops)))
 
 
+def rotation_factors(rot: numpy.ndarray, low: Optional[numpy.ndarray] = None,
+                     upp: Optional[numpy.ndarray] = None):
+    """Host side of ``Wavefunction.transform`` (wavefunction.py:838-909): (P, L, U, M) with
+    rot^H = P L U from ``scipy.linalg.lu`` and M the norb x norb matrix of column operators,
+    M = inv(U') - strict_lower(L') - 1, where L', U' are the Hermitian conjugates of the factors
+    with the diagonal moved into the upper one.  With external ``low``, ``upp`` (rot == low @
+    upp, the way back in the quadratic time evolution) they are used as they are."""
+
+    def transpose_matrix(low, upp):
+        ndim = low.shape[0]
+        lowt, uppt = low.astype(numpy.complex128), upp.astype(numpy.complex128)
+        for irow in range(ndim):
+            uppt[irow, irow + 1:] /= uppt[irow, irow]
+            lowt[irow, irow], uppt[irow, irow] = uppt[irow, irow], lowt[irow, irow]
+            for icol in range(irow):
+                lowt[irow, icol] *= lowt[icol, icol]
+        return uppt.T.conj(), lowt.T.conj()
+
+    def process_matrix(low, upp):
+        ndim = low.shape[0]
+        output = linalg.solve_triangular(upp, numpy.identity(ndim))
+        return output - numpy.tril(low, -1) - numpy.identity(ndim)
+
+    if low is None:
+        perm, low, upp = linalg.lu(rot.transpose().conjugate())
+        lowt, uppt = transpose_matrix(low, upp)
+        return perm, low, upp, process_matrix(lowt, uppt)
+    return None, low, upp, process_matrix(low, upp)
+
+
 class Wavefunction:
     """A state vector as a set of FqeData sectors keyed by (nele, m_s)."""
 
@@ -545,31 +575,7 @@ class Wavefunction:
         if external:
             assert numpy.allclose(rotation, low @ upp)
 
-        def ludecomp(rotmat):
-            return linalg.lu(rotmat.transpose().conjugate())
-
-        def transpose_matrix(low, upp):
-            # Hermitian conjugate of the factors with the diagonal moved into the upper one
-            ndim = low.shape[0]
-            lowt, uppt = low.astype(numpy.complex128), upp.astype(numpy.complex128)
-            for irow in range(ndim):
-                uppt[irow, irow + 1:] /= uppt[irow, irow]
-                lowt[irow, irow], uppt[irow, irow] = uppt[irow, irow], lowt[irow, irow]
-                for icol in range(irow):
-                    lowt[irow, icol] *= lowt[icol, icol]
-            return uppt.T.conj(), lowt.T.conj()
-
-        def process_matrix(low, upp):
-            ndim = low.shape[0]
-            output = linalg.solve_triangular(upp, numpy.identity(ndim))
-            return output - numpy.tril(low, -1) - numpy.identity(ndim)
-
-        def factors(rot, low, upp):
-            if low is None:
-                perm, low, upp = ludecomp(rot)
-                lowt, uppt = transpose_matrix(low, upp)
-                return perm, low, upp, process_matrix(lowt, uppt)
-            return None, low, upp, process_matrix(low, upp)
+        factors = rotation_factors
 
         if rotation.shape[0] == norb:
             perm, low, upp, output = factors(rotation, low, upp)

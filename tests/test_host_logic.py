@@ -171,3 +171,24 @@ def test_sparse_hamiltonian_normal_ordering_against_brute_force():
                                   ((4, 1), (4, 0)): 1.0}).is_individual()
     it = ham.iht(0.5)
     assert it.terms()[0][0] == -0.25j and ham.terms()[0][0] == 0.5
+
+
+def test_rotation_factors_match_oracle_and_reconstruct():
+    """host part of Wavefunction.transform: LU factors of rot^H and the column-operator matrix"""
+    from scipy.linalg import expm
+    from fqe_b200.wavefunction import rotation_factors
+    rng = np.random.default_rng(4)
+    for n in (2, 5, 8):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        rot = expm(-0.4j * (a + a.conj().T))
+        perm, low, upp, mat = rotation_factors(rot)
+        assert np.allclose(perm @ low @ upp, rot.conj().T, atol=1e-13)
+        operm, olow, oupp, lowt, uppt = O.lu_factors(rot)
+        assert np.array_equal(perm, operm) and np.allclose(low, olow) and np.allclose(upp, oupp)
+        assert np.allclose(mat, O.column_operator(lowt, uppt), atol=1e-13)
+        # the way back: external factors are taken as they are
+        back = (rot @ perm).conj().T
+        assert np.allclose(back, low @ upp, atol=1e-13)
+        _, l2, u2, mat2 = rotation_factors(back, low, upp)
+        assert l2 is low and u2 is upp
+        assert np.allclose(mat2, O.column_operator(low, upp), atol=1e-13)
