@@ -183,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "sigma/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------
@@ -489,14 +489,37 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": None, "unit": "sigma/s", "cores": host_cores(),
                                     "kind": "reference", "sample": f"unavailable: {exc}"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Send everything libraries write to stdout (NCCL prints its version banner there) to
+    stderr, and keep the original stdout for the ONE JSON line of the contract."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
