@@ -53,3 +53,28 @@ def test_fails_loudly_without_gpu():
     import fqe_b200
     with pytest.raises(L.FqeB200Error):
         fqe_b200.get_wavefunction(2, 0, 2)
+
+
+def test_plain_c_client_links_and_reports_missing_device(tmp_path):
+    """examples/c_client.c: the boundary is usable from plain C (no Python / torch / C++ in
+    the signatures).  It must compile against include/fqe_b200.h, link to the library and - in
+    a container without a GPU - get FQEB_ERR_NODEVICE instead of a CPU fallback."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "openfermion-fqe_b200", "fqe_b200", "lib")
+    exe = str(tmp_path / "c_client")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "c_client.c"), "-o", exe,
+                           "-L" + libdir, "-lfqe_b200", "-Wl,-rpath," + libdir, "-lm"])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "libfqe_b200 version" in res.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert "|sigma| =" in res.stdout
+    else:
+        assert "no device" in res.stdout and "no CPU fallback" in res.stdout
