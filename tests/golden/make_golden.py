@@ -165,6 +165,24 @@ def transform_goldens(fqe):
         # exact answer for the quadratic evolution from the dense one-particle picture:
         # <x| exp(-itH) |psi> checked through U = exp(-i t h1) as an orbital rotation
         out[f"{tag}_quad_unitary"] = expm(-1j * t * h1)
+    # block-diagonal 2norb x 2norb rotation: different unitaries for alpha and beta
+    n, sz, norb = 5, 1, 6
+    rng = np.random.default_rng(20260699)
+
+    def unitary():
+        a = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
+        return expm(-0.6j * (a + a.conj().T))
+
+    big = np.zeros((2 * norb, 2 * norb), dtype=np.complex128)
+    big[:norb, :norb], big[norb:, norb:] = unitary(), unitary()
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    c0 = rand_state(wfn.get_coeff((n, sz)).shape, rng)
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0.copy()})
+    perm, low, upp, res = wfn.transform(big)
+    out["tz_meta"] = np.array([n, sz, norb], dtype=np.int64)
+    out["tz_c0"], out["tz_rot"] = c0, big
+    out["tz_perm"], out["tz_low"], out["tz_upp"] = perm, low, upp
+    out["tz_transformed"] = res.get_coeff((n, sz))
     np.savez_compressed(os.path.join(HERE, "ref_transform.npz"), **out)
     print("ref_transform.npz", os.path.getsize(os.path.join(HERE, "ref_transform.npz")), "bytes")
 

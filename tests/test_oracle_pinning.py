@@ -295,3 +295,21 @@ def test_rdm_goldens(golden_dir, tag):
     for got, key in ((r1, "rdm1"), (r1, "rdm12_1"), (r2, "rdm12_2"), (t1, "trdm1"),
                      (t1, "trdm12_1"), (t2, "trdm12_2")):
         assert O.rel_err(got, z[f"{tag}_{key}"]) < TOL
+
+
+def test_spin_block_rotation_golden(golden_dir):
+    """Wavefunction.transform with a block-diagonal 2norb x 2norb rotation (different alpha and
+    beta unitaries), recorded from the reference (wavefunction.py:929-957)"""
+    z = np.load(os.path.join(golden_dir, "ref_transform.npz"))
+    n, sz, norb = [int(x) for x in z["tz_meta"]]
+    na = (n + sz) // 2
+    g = O.graph(na, n - na, norb)
+    rot = z["tz_rot"]
+    fa, fb = O.lu_factors(rot[:norb, :norb]), O.lu_factors(rot[norb:, norb:])
+    out = O.apply_columns_recursive(g, z["tz_c0"], O.column_operator(fa[3], fa[4]),
+                                    O.column_operator(fb[3], fb[4]))
+    assert O.rel_err(out, z["tz_transformed"]) < TOL
+    assert np.array_equal(z["tz_perm"][:norb, :norb], fa[0])
+    assert np.array_equal(z["tz_perm"][norb:, norb:], fb[0])
+    assert np.allclose(z["tz_low"][norb:, norb:], fb[1], atol=1e-14, rtol=0)
+    assert np.allclose(z["tz_upp"][:norb, :norb], fa[2], atol=1e-14, rtol=0)
