@@ -64,6 +64,8 @@ def parse_args():
                     "difference to the sharded + allreduced result")
     ap.add_argument("--cpu-budget", type=float, default=15.0,
                     help="seconds of CPU work per reference sample")
+    ap.add_argument("--ref-budget", type=float, default=300.0,
+                    help="--impl reference: seconds of full sigma builds (at least one is run)")
     return ap.parse_args()
 
 
@@ -138,17 +140,6 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # CPU arm: the reference's own C kernels on the host cores
 # ----------------------------------------------------------------------------------
-def cpu_sigma_seconds(norb, kind, budget_s):
-    from oracle import ref_harness as R
-    from fqe_b200 import synth
-    na = nb = norb // 2
-    g = R.graph(na, nb, norb)
-    h1, h2 = synth.integrals(norb, kind)
-    c = synth.state(g.lena, g.lenb, seed=synth.seed_for(norb, 50))
-    secs, desc = R.estimate_sigma_seconds(g, c, h1, h2, budget_s)
-    return secs, desc
-
-
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -156,34 +147,131 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """Give the reference's OpenMP loops every core this process may run on, whatever the
+    launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers), and keep BLAS from
+    nesting threads inside them.  Returns the OpenMP thread count actually in effect."""
+    import ctypes
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    from oracle import ref_harness as R
+    R.lib()                       # loads oracle/_ref/libfqe_ref*.so (and libgomp with it)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(cores)   # libgomp may have read the environment earlier
+        gomp.omp_get_max_threads.restype = ctypes.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return None
+
+
+def cpu_inputs(norb, kind):
+    from oracle import ref_harness as R
+    from fqe_b200 import synth
+    na = nb = norb // 2
+    g = R.graph(na, nb, norb)
+    h1, h2 = synth.integrals(norb, kind)
+    c = synth.state(g.lena, g.lenb, seed=synth.seed_for(norb, 50))
+    return R, g, c, h1, h2
+
+
+def cpu_sigma_seconds(norb, kind, budget_s):
+    """Bounded exact-work sample of one reference sigma, extrapolated (ref_harness)."""
+    R, g, c, h1, h2 = cpu_inputs(norb, kind)
+    return R.estimate_sigma_seconds(g, c, h1, h2, budget_s)
+
+
+def config_dict(norb, kind, shard, world, op_class=None):
+    """The same `config` keys in both arms (the driver compares them)."""
+    from math import comb
+    la = comb(norb, norb // 2)
+    cfg = {
+        "workload": workload_name(norb, kind), "norb": norb, "kind": kind,
+        "determinants": la * la, "shard": shard, "parallelism": f"{shard}{world}",
+        "l2": "inputs larger than L2 (C = %.2f GB, D/E chunks stream from HBM)" %
+              (la * la * 16 / 1e9),
+        "operator_class": op_class or ("real, pair-symmetric" if kind == "real8" else "complex"),
+    }
+    return cfg
+
+
 def run_reference(args):
+    """The reference's own C implementation of the path (oracle/_ref, compiled from
+    /root/reference/src/fqe/lib/*.c) on all host cores.  Every timed step is ONE FULL sigma
+    build at the benchmark size; as many of the requested steps as fit into --ref-budget
+    seconds are run (at least one) and `steps` reports how many did."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    times, desc = [], ""
-    # every step is one bounded exact-work sample of the full workload
-    for it in range(args.warmup + args.steps):
-        secs, desc = cpu_sigma_seconds(args.norb, args.kind, args.cpu_budget)
-        if it >= args.warmup:
-            times.append(secs)
+    threads = use_all_host_threads()
+    R, g, c, h1, h2 = cpu_inputs(args.norb, args.kind)
+    # warm-up: a small exact-work slice (loads the library, touches the tables and C)
+    R.time_sigma_sample(g, c, h1, h2, 16)
+    times = []
+    t_begin = time.perf_counter()
+    sig = None
+    while len(times) < max(1, args.steps):
+        if times and (time.perf_counter() - t_begin) + times[-1] > args.ref_budget:
+            break
+        t0 = time.perf_counter()
+        sig = R.sigma_restricted(g, c, h1, h2)
+        times.append(time.perf_counter() - t0)
     mean_s = sum(times) / len(times)
     value = 1.0 / mean_s
+    verify = verify_against_golden(sig, args.norb, args.kind, numpy_state=True)
+    del sig
+    est_s, est_desc = R.estimate_sigma_seconds(g, c, h1, h2, args.cpu_budget)
+    sample = ("%d full sigma build(s) of the whole workload, lm_apply_array12_same_spin_opt x2 + "
+              "lm_apply_array12_diff_spin_opt as FqeData._apply_array_spatial12_lm calls them; "
+              "OpenMP threads in effect = %s on %d usable cores; scipy BLAS zaxpy as in the "
+              "reference's Cython shim, BLAS itself single-threaded inside the OpenMP loops"
+              % (len(times), threads, cores))
     line = {
         "impl": "reference",
         "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": 0,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": 1e3 * mean_s, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.norb, args.kind), "norb": args.norb,
-                   "kind": args.kind},
-        "cpu_baseline": {"value": value, "unit": "sigma/s", "cores": cores, "kind": "reference",
-                         "sample": desc + "; OpenMP threads = all host cores; scipy BLAS zaxpy as "
-                         "in the reference's Cython shim"},
+        "config": config_dict(args.norb, args.kind, args.shard, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "sigma/s", "cores": cores,
+                         "omp_threads": threads, "kind": "reference", "sample": sample,
+                         "extrapolated": False, "step_seconds": times},
+        "sampled_estimate": {"value": 1.0 / est_s, "unit": "sigma/s", "extrapolated": True,
+                             "sample": est_desc},
+        "verify_rel_err": verify,
         "e2e": {"value": value, "unit": "sigma/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
+    if threads is not None and threads != cores:
+        line["cpu_baseline"]["warning"] = "OpenMP threads != usable cores"
     emit(line)
+
+
+def verify_against_golden(state, norb, kind, numpy_state=False):
+    """Worst relative deviation of `state` (the sigma of the benchmark inputs) from the
+    signature the UNMODIFIED reference produced in the build container
+    (tests/golden/ref_large.npz, tests/golden/make_golden_large.py); None if there is no
+    signature for this size."""
+    try:
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden_large as GL
+        with np.load(os.path.join(ROOT, "tests", "golden", "ref_large.npz")) as z:
+            tag = f"sigma{norb}_{kind}"
+            if f"{tag}_norm" not in z.files:
+                return None
+            sig = GL.stored_signature(z, tag)
+            sig = {k: np.array(v) for k, v in sig.items()}
+        seed = int(sig["seed"][0])
+        got = GL.signature(state, seed) if numpy_state else GL.signature_torch(state, seed)
+        return float(GL.signature_error(sig, got)[0])
+    except Exception as exc:  # the checker must not take the measurement down
+        sys.stderr.write(f"verify_against_golden: {exc}\n")
+        return None
 
 
 # ----------------------------------------------------------------------------------
@@ -262,6 +350,9 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     checksum = float(torch.view_as_real(sigma).abs().sum().item())
+    # the timed sigma against the reference's own result for these inputs (always on: it is
+    # a few reductions on the device, outside the timed region)
+    golden_verify = verify_against_golden(sigma, norb, kind)
     verify = None
     if args.verify:
         full = sector.apply_operator(op)
@@ -274,7 +365,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         "ms_total": ms_max, "launches": int(launches),
         "phase_ms": [float(x) for x in ms3], "phase_launches": [int(x) for x in cnt3],
         "rows": rows, "pairs": pairs, "la": la, "lb": lb, "clocks": clocks,
-        "checksum": checksum, "verify": verify,
+        "checksum": checksum, "verify": verify, "golden_verify": golden_verify,
     }
 
     if do_e2e:
@@ -426,17 +517,14 @@ def run_b200(args):
         "ms_per_step": main["ms_total"] / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": workload_name(args.norb, args.kind), "norb": args.norb,
-            "determinants": main["la"] * main["lb"], "shard": args.shard,
-            "parallelism": f"{args.shard}{world}",
-            "l2": "inputs larger than L2 (C = %.2f GB, D/E chunks stream from HBM)" %
-                  (main["la"] * main["lb"] * 16 / 1e9),
-            "operator_class": {L.OP_REAL: "real", L.OP_IMAG: "imag", L.OP_COMPLEX: "complex"}[
-                main["op_kind"]] + (", pair-symmetric" if main["op_sym"] else ""),
-        },
+        "config": config_dict(
+            args.norb, args.kind, args.shard, world,
+            {L.OP_REAL: "real", L.OP_IMAG: "imag", L.OP_COMPLEX: "complex"}[main["op_kind"]] +
+            (", pair-symmetric" if main["op_sym"] else "")),
         "gpu_launches": main["launches"],
-        "verify_rel_err": main["verify"], "e2e_verify_rel_err": main.get("e2e_verify"),
+        "verify_rel_err": main["golden_verify"], "verify_against": "signature of the UNMODIFIED "
+        "reference's sigma for these inputs (tests/golden/ref_large.npz)",
+        "shard_verify_rel_err": main["verify"], "e2e_verify_rel_err": main.get("e2e_verify"),
         "clocks": main["clocks"],
         "e2e": {"value": args.steps / main["e2e_s"], "unit": "sigma/s",
                 "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
@@ -482,9 +570,14 @@ def run_b200(args):
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            threads = use_all_host_threads()
             secs, desc = cpu_sigma_seconds(args.norb, args.kind, args.cpu_budget)
             line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "sigma/s", "cores": host_cores(),
-                                    "kind": "reference", "sample": desc}
+                                    "omp_threads": threads, "kind": "reference",
+                                    "extrapolated": True,
+                                    "sample": desc + "; the full-size measurement is the "
+                                    "`--impl reference` arm (this bounded sample under-states the "
+                                    "reference's time at full size, see DESIGN.md 7)"}
         except Exception as exc:  # the checker is optional for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "sigma/s", "cores": host_cores(),
                                     "kind": "reference", "sample": f"unavailable: {exc}"}

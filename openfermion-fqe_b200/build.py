@@ -28,27 +28,64 @@ FLAGS = [
 ]
 
 
+HEADERS = [os.path.join(ROOT, "include", "fqe_b200.h")]
+OBJ_DIR = os.path.join(HERE, "build", "obj")
+
+
+def _headers():
+    return HEADERS + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+        [os.path.abspath(__file__)]
+
+
 def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps += [os.path.join(ROOT, "include", "fqe_b200.h"), os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + _headers()
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(args):
+    src, obj, defines, verbose = args
+    cmd = [NVCC] + [f for f in FLAGS if f != "-shared"] + ["-D" + d for d in defines] + \
+        ["-c", src, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, res
+
+
 def build(force=False, verbose=False, defines=(), out=None):
+    """One object per source file (compiled in parallel, rebuilt only when the source or a
+    header changed), linked into the shared library."""
     if out is None and not force and not stale():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OUT_DIR, exist_ok=True)
+    variant = "default" if not defines else "_".join(sorted(defines)).replace("=", "-")
+    obj_dir = os.path.join(OBJ_DIR, variant)
+    os.makedirs(obj_dir, exist_ok=True)
     out = out or OUT
-    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    jobs, objs = [], []
+    for name in SOURCES:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(obj_dir, name.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or not os.path.exists(obj) or \
+                os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, obj, tuple(defines), verbose))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4) or 1) as pool:
+        for src, res in pool.map(_compile_one, jobs):
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed compiling {os.path.basename(src)}")
+    link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin",
+            "/usr/bin/g++", "-cudart", "static"] + objs + ["-o", out]
+    res = subprocess.run(link, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libfqe_b200.so")
+        raise RuntimeError("nvcc failed linking libfqe_b200.so")
     return out
 
 

@@ -169,7 +169,11 @@ static int dc_run(const fqeb_graph *g, const double *h_diag, const double *h_arr
   const int norb = g->norb;
   if (norb == 0) return FQEB_OK;
   const int nd = norb, nv = norb * norb;
-  double2 *d_diag = (double2 *)g->d_small;
+  cudaStream_t st_key = st;
+  GraphScratch sc;
+  rc = graph_scratch(g, st_key, &sc);
+  if (rc != FQEB_OK) return rc;
+  double2 *d_diag = (double2 *)sc.small;
   double2 *d_v = d_diag + 64;
   double2 *d_diag_e = d_v + 64 * 64;
   double2 *d_v_e = d_diag_e + 64;
@@ -188,11 +192,11 @@ static int dc_run(const fqeb_graph *g, const double *h_diag, const double *h_arr
   for (int s = 0; s < nspin; ++s) {
     const unsigned blocks = (unsigned)((g->len[s] + 255) / 256);
     k_dc_string_terms<EVOLVE><<<blocks, 256, 0, st>>>(norb, g->len[s], g->d_str[s], use_diag,
-                                                      use_v, (double2 *)g->d_sterm[s]);
+                                                      use_v, (double2 *)sc.sterm[s]);
     FQEB_CHECK_LAUNCH();
   }
-  const double2 *aterm = (const double2 *)g->d_sterm[0];
-  const double2 *bterm = (const double2 *)g->d_sterm[g->shared_spin ? 0 : 1];
+  const double2 *aterm = (const double2 *)sc.sterm[0];
+  const double2 *bterm = (const double2 *)sc.sterm[g->shared_spin ? 0 : 1];
   const size_t tab_bytes = sizeof(double2) * 256 * (size_t)((norb + 7) / 8);
   // persistent grid: exactly the CTAs that are resident at once, so that every CTA walks the
   // same number of rows (8 CTAs per SM with only 3 resident left a 2/3-empty last wave)

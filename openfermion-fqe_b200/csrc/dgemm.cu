@@ -42,6 +42,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -1275,8 +1276,10 @@ namespace fqeb {
 // Contraction operand for a sector with n_elec electrons: h2' in the operator's pair space
 // (same layout as fqeb_op::d_A) with the one-body term absorbed into the diagonal-pair
 // columns.  Built on first use and cached per n_elec.
+static std::mutex g_operand_cache_mu;   // guards every operator's fused_cache map
 int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A) {
   FQEB_REQUIRE(op->absorb_ok && n_elec > 0, "absorbed_operand: one-body term not absorbable");
+  std::lock_guard<std::mutex> lock(g_operand_cache_mu);
   auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
   auto it = cache->find(n_elec);
   if (it != cache->end()) {

@@ -53,6 +53,19 @@ int upload_finish();
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// scratch set of `stream` for graph g (allocated on first use, thread-safe)
+struct GraphScratch {
+  double *small;
+  double *sterm[2];
+};
+int graph_scratch(const fqeb_graph *g, cudaStream_t stream, GraphScratch *out);
+// RAII lock of the graph's mutex (lazy tables such as the occupancy lists)
+struct GraphLock {
+  explicit GraphLock(const fqeb_graph *g);
+  ~GraphLock();
+  void *mu;
+};
+
 constexpr int kMaxOrb = 63;  // as the reference C path (settings.py c_string_max_norb)
 
 }  // namespace fqeb
@@ -94,9 +107,14 @@ struct fqeb_graph {
   int lk[2];
   int2 *d_clistT[2];       // [len][lk]   by string  (warp-uniform access per row)
   int2 *d_clist[2];        // [lk][len]   by slot    (coalesced access per column)
-  double *d_small;         // scratch for small operator uploads (diag, v, ...)
+  // Scratch of the diagonal / column / n-body entry points: one set PER CUDA STREAM (graphs are
+  // shared process-wide per sector and device, and two sectors' calls may be in flight on
+  // different streams or host threads).  d_small / d_sterm are the first set; the others hang
+  // off `sync` and are handed out by fqeb::graph_scratch().
+  double *d_small;         // small operator uploads (diag, v, ...)
   size_t small_bytes;
-  double *d_sterm[2];      // per-string diagonal-Coulomb terms, complex [len]
+  double *d_sterm[2];      // per-string terms / by-target tables, 16 bytes per string
+  void *sync;              // fqeb::GraphSync*: mutex + per-stream scratch sets + lazy-table guard
   // ordered lists of the strings with orbital icol occupied / empty, built on first use by
   // the column-rotation kernels (rotate.cu): [norb][C(norb-1,nele-1)] / [norb][C(norb-1,nele)]
   int32_t *d_occ[2], *d_unocc[2];

@@ -11,11 +11,55 @@
 // entry, so the tables for norb=16 (2 x 13 MB) are built in well under a ms.
 #include "fqeb_common.cuh"
 
+#include <map>
+#include <mutex>
+
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 namespace fqeb {
+
+// mutex + per-stream scratch sets of a graph (see fqeb_graph::sync)
+struct GraphSync {
+  std::mutex mu;
+  std::map<cudaStream_t, GraphScratch> sets;
+};
+
+int graph_scratch(const fqeb_graph *g, cudaStream_t stream, GraphScratch *out) {
+  GraphSync *sy = static_cast<GraphSync *>(g->sync);
+  std::lock_guard<std::mutex> lock(sy->mu);
+  auto it = sy->sets.find(stream);
+  if (it != sy->sets.end()) {
+    *out = it->second;
+    return FQEB_OK;
+  }
+  GraphScratch sc{nullptr, {nullptr, nullptr}};
+  if (sy->sets.empty()) {
+    // the first stream that shows up gets the set allocated with the graph
+    sc.small = g->d_small;
+    sc.sterm[0] = g->d_sterm[0];
+    sc.sterm[1] = g->d_sterm[1];
+  } else {
+    if (cudaMalloc(&sc.small, g->small_bytes) != cudaSuccess ||
+        cudaMalloc(&sc.sterm[0], sizeof(double) * 2 * (g->len[0] > 0 ? g->len[0] : 1)) != cudaSuccess ||
+        cudaMalloc(&sc.sterm[1], sizeof(double) * 2 * (g->len[1] > 0 ? g->len[1] : 1)) != cudaSuccess) {
+      if (sc.small) cudaFree(sc.small);
+      if (sc.sterm[0]) cudaFree(sc.sterm[0]);
+      set_error("graph_scratch: cannot allocate a scratch set for a new stream");
+      return FQEB_ERR_NOMEM;
+    }
+  }
+  sy->sets[stream] = sc;
+  *out = sc;
+  return FQEB_OK;
+}
+
+GraphLock::GraphLock(const fqeb_graph *g) : mu(&static_cast<GraphSync *>(g->sync)->mu) {
+  static_cast<std::mutex *>(mu)->lock();
+}
+GraphLock::~GraphLock() { static_cast<std::mutex *>(mu)->unlock(); }
+
 
 static void host_binom(uint64_t *b /*[65*65]*/) {
   for (int n = 0; n < 65; ++n) {
@@ -244,6 +288,7 @@ extern "C" int fqeb_graph_create(int norb, int nalpha, int nbeta, fqeb_graph **o
     rc = build_spin(g, spin, d_binom);
     if (rc != FQEB_OK) return fail(rc);
   }
+  g->sync = new GraphSync();
   g->small_bytes = sizeof(double) * 2 * (size_t)(4 * 64 * 64 + 4 * 64);
   if (cudaMalloc(&g->d_small, g->small_bytes) != cudaSuccess ||
       cudaMalloc(&g->d_sterm[0], sizeof(double) * 2 * g->len[0]) != cudaSuccess ||
@@ -293,6 +338,16 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
     if (g->d_clist[s]) cudaFree(g->d_clist[s]);
   }
   for (int s = 0; s < 2; ++s) free(g->h_Z[s]);
+  if (g->sync) {
+    GraphSync *sy = static_cast<GraphSync *>(g->sync);
+    for (auto &kv : sy->sets) {
+      if (kv.second.small == g->d_small) continue;   // the graph's own set, freed below
+      cudaFree(kv.second.small);
+      cudaFree(kv.second.sterm[0]);
+      cudaFree(kv.second.sterm[1]);
+    }
+    delete sy;
+  }
   if (g->d_small) cudaFree(g->d_small);
   if (g->d_pairs_id) cudaFree(g->d_pairs_id);
   for (int s = 0; s < 2; ++s)

@@ -141,8 +141,11 @@ extern "C" int fqeb_nbody_accumulate(const fqeb_graph *g, double zr, double zi, 
   if (rc != FQEB_OK) return rc;
   const int64_t lena = g->len[0], lenb = g->len[1];
   cudaStream_t st = (cudaStream_t)stream;
-  // by-target tables live in the per-string scratch of the graph (16 bytes per string)
-  int32_t *inva = (int32_t *)g->d_sterm[0], *invb = (int32_t *)g->d_sterm[1];
+  // by-target tables live in this stream's per-string scratch of the graph (16 bytes per string)
+  GraphScratch sc;
+  rc = graph_scratch(g, st, &sc);
+  if (rc != FQEB_OK) return rc;
+  int32_t *inva = (int32_t *)sc.sterm[0], *invb = (int32_t *)sc.sterm[1];
   const int64_t lmax = lena > lenb ? lena : lenb;
   k_nbody_invmap<<<dim3((unsigned)((lmax + kNB - 1) / kNB), 2), kNB, 0, st>>>(
       g->norb, lena, lenb, g->d_str[0], g->d_str[1], g->d_Z[0], g->d_Z[1], oa, ob, inva, invb);

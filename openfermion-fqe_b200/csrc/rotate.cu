@@ -195,11 +195,16 @@ static int64_t binom_i64(int n, int k) {
 
 // occupancy lists of one spin, built on first use:
 // d_occ[spin][icol][.] strings with icol occupied, d_unocc[spin][icol][.] with icol empty
+static int ensure_lists_locked(const fqeb_graph *cg, int spin);
 static int ensure_lists(const fqeb_graph *cg, int spin) {
+  GraphLock lock(cg);   // lazily built, shared by every sector of this graph
+  return ensure_lists_locked(cg, spin);
+}
+static int ensure_lists_locked(const fqeb_graph *cg, int spin) {
   fqeb_graph *g = const_cast<fqeb_graph *>(cg);
   if (g->d_occ[spin]) return FQEB_OK;
   if (spin == 1 && g->shared_spin) {
-    int rc = ensure_lists(cg, 0);
+    int rc = ensure_lists_locked(cg, 0);
     if (rc != FQEB_OK) return rc;
     g->d_occ[1] = g->d_occ[0];
     g->d_unocc[1] = g->d_unocc[0];
@@ -239,6 +244,9 @@ extern "C" int fqeb_apply_columns(const fqeb_graph *g, int spin, const double *h
   rc = ensure_lists(g, spin);
   if (rc != FQEB_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  GraphScratch sc;
+  rc = graph_scratch(g, st, &sc);
+  if (rc != FQEB_OK) return rc;
   // device copy of the matrix, transposed so that column icol is contiguous
   std::vector<double> mt(2 * (size_t)norb * norb);
   for (int i = 0; i < norb; ++i)
@@ -246,10 +254,10 @@ extern "C" int fqeb_apply_columns(const fqeb_graph *g, int spin, const double *h
       mt[2 * ((size_t)c * norb + i)] = h_mat[2 * ((size_t)i * norb + c)];
       mt[2 * ((size_t)c * norb + i) + 1] = h_mat[2 * ((size_t)i * norb + c) + 1];
     }
-  FQEB_CUDA(cudaMemcpyAsync(g->d_small, mt.data(), sizeof(double) * mt.size(),
+  FQEB_CUDA(cudaMemcpyAsync(sc.small, mt.data(), sizeof(double) * mt.size(),
                             cudaMemcpyHostToDevice, st));
   FQEB_CUDA(cudaStreamSynchronize(st));  // mt is a stack-lifetime staging buffer
-  const double2 *d_mt = (const double2 *)g->d_small;
+  const double2 *d_mt = (const double2 *)sc.small;
   double2 *c = (double2 *)d_coeff;
   const int64_t nocc = binom_i64(norb - 1, nele - 1), nun = binom_i64(norb - 1, nele);
   const int nbt = (int)((lenb + kRB - 1) / kRB);
@@ -303,11 +311,14 @@ static int diagonal_common(const fqeb_graph *g, const double *h_aarray, const do
     both[i] = h_aarray[i];
     both[2 * norb + i] = h_barray[i];
   }
-  FQEB_CUDA(cudaMemcpyAsync(g->d_small, both.data(), sizeof(double) * both.size(),
+  GraphScratch sc;
+  int rc = graph_scratch(g, st, &sc);
+  if (rc != FQEB_OK) return rc;
+  FQEB_CUDA(cudaMemcpyAsync(sc.small, both.data(), sizeof(double) * both.size(),
                             cudaMemcpyHostToDevice, st));
   FQEB_CUDA(cudaStreamSynchronize(st));
-  const double2 *da = (const double2 *)g->d_small, *db = da + norb;
-  double2 *fa = (double2 *)g->d_sterm[0], *fb = (double2 *)g->d_sterm[1];
+  const double2 *da = (const double2 *)sc.small, *db = da + norb;
+  double2 *fa = (double2 *)sc.sterm[0], *fb = (double2 *)sc.sterm[1];
   const int threads = 256;
   if (evolve) {
     k_string_diag<true><<<(unsigned)((lena + threads - 1) / threads), threads, 0, st>>>(
