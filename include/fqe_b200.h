@@ -188,6 +188,17 @@ int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta,
                                const double *h_h1p, const double *h_h2p,
                                const double *h_coeff, double *h_sigma);
 
+/* Which contraction path the most recent two-body fqeb_sigma_restricted call took (a test /
+ * benchmark aid; the result is the same sigma to the tolerance of the path):
+ *   FQEB_PATH_THREE_KERNEL  gather -> FP64 DMMA GEMM -> scatter, D and E through HBM
+ *   FQEB_PATH_FUSED         gather fused into the FP64 DMMA contraction (D stays on chip)
+ *   FQEB_PATH_SLICED        gather fused into the INT8-sliced tcgen05 contraction (csrc/ozaki.cu):
+ *                           default for real / imaginary operators with a pair space <= 144 when
+ *                           the state's estimated quantisation error is below FQEB_OZAKI_TOL
+ *                           (environment, default 5e-12); FQEB_OZAKI=0 disables it.            */
+enum { FQEB_PATH_NONE = 0, FQEB_PATH_THREE_KERNEL = 1, FQEB_PATH_FUSED = 2, FQEB_PATH_SLICED = 3 };
+int fqeb_sigma_last_path(void);
+
 /* Per-kernel device timing of the sigma build (bench.py's roofline leg).  When
  * enabled, fqeb_sigma_restricted brackets every gather / contraction / scatter
  * launch with CUDA events on the launching stream.  fqeb_profile_collect

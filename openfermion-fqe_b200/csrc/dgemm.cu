@@ -1329,9 +1329,14 @@ int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A) {
 // Device buffers are returned with cudaFreeAsync on `stream`: the release is ordered after the
 // work already enqueued there (the kernels that may still read the operator) and does not
 // synchronise the device.
+namespace fqeb {
+void ozaki_forget(const fqeb_op *op, cudaStream_t st);
+}
+
 extern "C" int fqeb_op_destroy_async(fqeb_op *op, void *stream) {
   if (!op) return FQEB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  fqeb::ozaki_forget(op, st);
   if (op->fused_cache) {
     auto *cache = static_cast<std::map<int, double *> *>(op->fused_cache);
     for (auto &kv : *cache) cudaFreeAsync(kv.second, st);

@@ -1,0 +1,692 @@
+// INT8-sliced two-electron contraction on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// Same mathematics as k_sigma_fused (dgemm.cu): for a chunk of alpha rows
+//
+//     E[kl, det] = sum_ij A[kl, ij] * D[ij, det],   D[ij, det] = +-C[y_a, b] +- C[a, y_b]
+//
+// (reference: numpy.einsum("ijkl,klmn->ijmn", h2e, dvec), src/fqe/fqe_data.py:656, on the dvec of
+// fqe_data.py:2209-2234; D is gathered on the fly and never reaches HBM).  sm_100a has no
+// tcgen05 path for FP64 and the DMMA contraction already runs at ~90 % of the
+// 37 TFLOP/s FP64 issue limit, so this kernel takes the only route past that roofline: the FP64
+// product is evaluated EXACTLY in integer arithmetic on digit slices (an Ozaki-type scheme):
+//
+//     C / S = sum_i c_i R^-(i+1),   A / T = sum_j a_j R^-(j+1),   R = 127, |c_i|, |a_j| <= 63
+//     D digits = +-c_i(alpha source) +- c_i(beta source)           |.| <= 126: int8
+//     E = S T sum_{i+j <= DMAX} R^-(i+j+2) (a_j . d_i)             int8 x int8 -> int32, exact
+//
+// with NS = 6 slices and DMAX = 5 (21 slice products).  The only errors are the two
+// quantisations (relative 127^-6 / 2 = 1.2e-13 of max|C| and of max|A|) and the dropped products
+// i + j > DMAX (same order); measured against the FP64 oracle: 1.3e-12 relative on sigma for
+// uniform random states (profiles/microbench/ozaki_proto.py).  The state's scale is GLOBAL, so a
+// state dominated by a few determinants loses relative accuracy on its small coefficients;
+// sigma.cu therefore takes this path only when  127^-6 * max|C| * sqrt(ndet) / ||C||  is below
+// a threshold and the FP64 DMMA kernels otherwise (both are parity-tested).
+//
+// Kernel anatomy (one persistent CTA per SM, 17 warps):
+//   * the digit planes of the operand A (B operand of the MMA: N = pairs kl, K = pairs ij) are
+//     copied once per CTA into shared memory in the canonical K-major no-swizzle UMMA layout;
+//   * per tile (one alpha row x 64 beta strings = 128 real rows m = (det, re|im)), 16 worker
+//     warps gather the 8-byte digit words of the alpha and the beta source of every (m, ij) from
+//     the pre-sliced coefficient planes, add them as packed biased bytes, transpose 4 x 4 bytes
+//     with PRMT and store 16-byte core-matrix rows of the D^T tile (A operand: M = 128, K = ij);
+//   * ONE thread issues the 21 x K/32 tcgen05.mma kind::i8 instructions of the tile, diagonal by
+//     diagonal (d = i + j) into three rotating 144-column accumulators in TMEM;
+//   * the same 16 warps drain the accumulators two diagonals at a time (acc_d * 127 + acc_{d+1}
+//     fits int32), convert to FP64, apply the weights and stream E out, overlapped with the MMAs
+//     of the following diagonals.
+#include "fqeb_common.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace fqeb {
+
+constexpr int OZ_NS = 6;           // digit slices of C and of the operand
+constexpr int OZ_DMAX = 5;         // slice products (i, j) with i + j <= OZ_DMAX are kept
+constexpr int OZ_RADIX = 127;
+constexpr int OZ_NMAX = 144;       // largest pair space (MMA N and K)
+constexpr int OZ_SLOT = 144;       // TMEM columns per accumulator slot
+constexpr int OZ_WORKERS = 512;    // 16 worker warps: producers, then epilogue
+constexpr int OZ_THREADS = OZ_WORKERS + 128;   // + one warpgroup: MMA issuer (3 warps idle)
+constexpr int OZ_TILE_DETS = 64;   // determinants per tile (128 real rows)
+
+// ---------------------------------------------------------------------------------------
+// coefficient digit planes
+// ---------------------------------------------------------------------------------------
+// planes[(sign*2 + part) * ndet + det] : 8 bytes, byte s = biased digit (d_s + 64) of slice s of
+// the real (part 0) / imaginary (part 1) part of +C (sign 0) or -C (sign 1); bytes 6, 7 = 64.
+// Biased digits of two sources add without carries between bytes (<= 254), and
+// (sum ^ 0x80) is the two's-complement sum of the two signed digits.
+
+__global__ void k_absmax_sumsq(int64_t n2, const double *__restrict__ x, double *__restrict__ part) {
+  // part[2*block] = max |x|, part[2*block+1] = sum x^2 over this block's grid-stride share
+  double mx = 0.0, ss = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    mx = fmax(mx, fabs(v));
+    ss += v * v;
+  }
+  __shared__ double s_mx[32], s_ss[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_mx[warp] = mx;
+    s_ss[warp] = ss;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    mx = lane < nw ? s_mx[lane] : 0.0;
+    ss = lane < nw ? s_ss[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      part[2 * blockIdx.x] = mx;
+      part[2 * blockIdx.x + 1] = ss;
+    }
+  }
+}
+
+__global__ void k_absmax_sumsq_final(int nblocks, const double *__restrict__ part,
+                                     double *__restrict__ out) {
+  // deterministic second pass: out[0] = max, out[1] = sum of squares, out[2] = scale S
+  double mx = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    mx = fmax(mx, part[2 * i]);
+    ss += part[2 * i + 1];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (threadIdx.x == 0) {
+    out[0] = mx;
+    out[1] = ss;
+    out[2] = 2.0001 * mx;   // |x| / S < 0.5: inside the range of OZ_NS balanced digits
+  }
+}
+
+__device__ __forceinline__ uint64_t balanced_digits(double x, double scale_pow) {
+  // biased digit bytes (most significant slice in byte 0) of x, |x| < 0.5
+  long long n = __double2ll_rn(x * scale_pow);
+  uint64_t w = 0x4040000000000000ull;   // bytes 6, 7: digit 0
+#pragma unroll
+  for (int s = OZ_NS - 1; s >= 0; --s) {
+    long long q = n / OZ_RADIX;
+    long long d = n - q * OZ_RADIX;               // truncated remainder in (-127, 127)
+    if (d > 63) {
+      d -= OZ_RADIX;
+      q += 1;
+    } else if (d < -63) {
+      d += OZ_RADIX;
+      q -= 1;
+    }
+    n = q;
+    w |= (uint64_t)(d + 64) << (8 * s);
+  }
+  return w;
+}
+
+__global__ void k_slice_coeff(int64_t ndet, const double2 *__restrict__ coeff,
+                              const double *__restrict__ stats, uint64_t *__restrict__ planes) {
+  const double s = stats[2];
+  const double inv = s > 0.0 ? 1.0 / s : 0.0;
+  double pw = 1.0;
+#pragma unroll
+  for (int i = 0; i < OZ_NS; ++i) pw *= (double)OZ_RADIX;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ndet;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 c = coeff[i];
+    const uint64_t re = balanced_digits(c.x * inv, pw), im = balanced_digits(c.y * inv, pw);
+    const uint64_t k128 = 0x8080808080808080ull;
+    planes[i] = re;
+    planes[ndet + i] = im;
+    planes[2 * ndet + i] = k128 - re;   // digits of -x: no borrow between bytes (every byte <= 127)
+    planes[3 * ndet + i] = k128 - im;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// operand digit planes (host side, cached per operator and electron count)
+// ---------------------------------------------------------------------------------------
+struct OzOperand {
+  int8_t *d_img;     // shared-memory image: [slice][kcol][row group][8][16] + zero block
+  size_t img_bytes;
+  double scale;      // T
+  int np, kc, ng, n_mma;
+};
+
+static std::mutex g_oz_mu;
+static std::map<std::pair<const fqeb_op *, int>, OzOperand> g_oz_cache;
+
+int absorbed_operand(const fqeb_op *op, int n_elec, const double **d_A);
+
+static void host_digits(double x, double scale_pow, int8_t *out) {
+  long long n = llrint(x * scale_pow);
+  for (int s = OZ_NS - 1; s >= 0; --s) {
+    long long q = n / OZ_RADIX, d = n - q * OZ_RADIX;
+    if (d > 63) {
+      d -= OZ_RADIX;
+      q += 1;
+    } else if (d < -63) {
+      d += OZ_RADIX;
+      q -= 1;
+    }
+    n = q;
+    out[s] = (int8_t)d;
+  }
+}
+
+bool ozaki_shape_ok(const fqeb_op *op) {
+  return op->has_h2 && op->kind != FQEB_OP_COMPLEX && op->absorb_ok && op->np >= 1 &&
+         op->np <= OZ_NMAX;
+}
+
+// digit image of the contraction operand with the one-body term absorbed (same matrix as
+// absorbed_operand builds for the DMMA kernels)
+static int ozaki_operand(const fqeb_op *op, int n_elec, OzOperand *out) {
+  std::lock_guard<std::mutex> lock(g_oz_mu);
+  auto key = std::make_pair(op, n_elec);
+  auto it = g_oz_cache.find(key);
+  if (it != g_oz_cache.end()) {
+    *out = it->second;
+    return FQEB_OK;
+  }
+  const int norb = op->norb, npair = norb * norb, np = op->np;
+  auto pair_of = [&](int c) {
+    if (!op->sym) return c;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= c) ++i;
+    return i * norb + (c - i * (i + 1) / 2);
+  };
+  const int part = op->kind == FQEB_OP_IMAG ? 1 : 0;
+  std::vector<double> a((size_t)np * np);
+  double amax = 0.0;
+  for (int c = 0; c < np; ++c)
+    for (int d = 0; d < np; ++d) {
+      const int ij = pair_of(c), kl = pair_of(d);
+      double v = op->h_h2p[2 * ((size_t)ij * npair + kl) + part];
+      if (kl / norb == kl % norb) v += op->h_h1p[2 * ij + part] / (double)n_elec;
+      a[(size_t)c * np + d] = v;
+      amax = fmax(amax, fabs(v));
+    }
+  OzOperand o;
+  o.np = np;
+  o.kc = (np + 15) / 16;
+  o.ng = (np + 7) / 8;
+  o.n_mma = (np + 15) / 16 * 16;
+  o.scale = 2.0001 * amax;
+  const size_t plane = (size_t)o.kc * o.ng * 128;
+  const size_t zero_block = (size_t)(o.n_mma / 8) * 128 + 128;
+  o.img_bytes = OZ_NS * plane + zero_block;
+  std::vector<int8_t> img(o.img_bytes, 0);
+  if (amax > 0.0) {
+    double pw = 1.0;
+    for (int i = 0; i < OZ_NS; ++i) pw *= (double)OZ_RADIX;
+    int8_t dg[OZ_NS];
+    for (int n = 0; n < np; ++n)        // row of the operand = output pair kl
+      for (int k = 0; k < np; ++k) {    // contraction index ij
+        host_digits(a[(size_t)n * np + k] / o.scale, pw, dg);
+        const size_t off = ((size_t)(k >> 4) * o.ng + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15);
+        for (int s = 0; s < OZ_NS; ++s) img[s * plane + off] = dg[s];
+      }
+  }
+  void *dev = nullptr;
+  int rc = upload_alloc(&dev, img.data(), img.size());
+  if (rc == FQEB_OK) rc = upload_finish();
+  if (rc != FQEB_OK) return rc;
+  o.d_img = (int8_t *)dev;
+  g_oz_cache[key] = o;
+  *out = o;
+  return FQEB_OK;
+}
+
+// called from fqeb_op_destroy_async: drop the cached images of this operator
+void ozaki_forget(const fqeb_op *op, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_oz_mu);
+  for (auto it = g_oz_cache.begin(); it != g_oz_cache.end();) {
+    if (it->first.first == op) {
+      cudaFreeAsync(it->second.d_img, st);
+      it = g_oz_cache.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t oz_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nOZ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra OZ_DONE;\nbra OZ_WAIT;\nOZ_DONE:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t oz_ldg64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int oz_ldg32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+#define OZ_TMEM_LD16(r, addr)                                                                  \
+  asm volatile(                                                                                \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13," \
+      "%14,%15}, [%16];"                                                                       \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),    \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),             \
+        "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                                  \
+      : "r"(addr))
+#define OZ_TMEM_LD8(r, addr)                                                                \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"      \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),      \
+                 "=r"(r[6]), "=r"(r[7])                                                       \
+               : "r"(addr))
+#define OZ_TMEM_LD4(r, addr)                                                      \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"      \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])                   \
+               : "r"(addr))
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+struct OzParams {
+  const int8_t *img;        // operand digit image (global)
+  int img_bytes;
+  int np, kc, ng, n_mma;    // pair space, 16-byte K columns, 8-row groups, MMA N
+  const uint64_t *planes;   // coefficient digit planes [4][ndet]
+  int64_t ndet;
+  const int32_t *mapT_a;    // [lena][ntab]  alpha adjoint map, by string
+  const int32_t *map_b;     // [ntab][lenb]  beta adjoint map, by pair
+  int ntab;
+  int64_t lenb, row0;
+  int pitch, tiles_per_row;
+  int64_t ntiles;
+  double2 *E;
+  int64_t lde;
+  const double *stats;      // stats[2] = S (scale of the coefficient digits)
+  double op_scale;          // T
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar[8];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kc = p.kc, ng = p.ng;
+  const uint32_t d_bytes = (uint32_t)OZ_NS * kc * 2048;   // D^T tile: [slice][kcol][16 groups][128]
+  uint8_t *s_d = smem;
+  uint8_t *s_b = smem + d_bytes;                           // operand image follows the tile
+  const uint32_t bar_dfull = oz_smem_u32(&s_bar[0]), bar_dfree = oz_smem_u32(&s_bar[1]);
+  const uint32_t bar_sfull = oz_smem_u32(&s_bar[2]), bar_sfree = oz_smem_u32(&s_bar[5]);
+
+  // one-time setup: operand image -> shared memory, barriers, TMEM
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_b);
+    for (int i = tid; i < p.img_bytes / 16; i += OZ_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    oz_mbar_init(bar_dfull, OZ_WORKERS);
+    oz_mbar_init(bar_dfree, 1);
+    for (int s = 0; s < 3; ++s) {
+      oz_mbar_init(bar_sfull + 8 * s, 1);
+      oz_mbar_init(bar_sfree + 8 * s, OZ_WORKERS / 32);
+    }
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        oz_smem_u32(&s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const int64_t my_tiles =
+      (int64_t)blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp >= 16) {
+    // ================================ MMA issuer ======================================
+    // this warpgroup hands its registers to the workers (5 warps per scheduler at launch
+    // leave 96 registers per thread; the workers need ~110 for 36 running FP64 sums)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (warp == 16 && lane == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t d_base = oz_smem_u32(s_d), b_base = oz_smem_u32(s_b);
+      const uint32_t b_plane = (uint32_t)kc * ng * 128;
+      const uint32_t zero_base = b_base + OZ_NS * b_plane;
+      const int ksteps = (kc + 1) / 2;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        oz_mbar_wait(bar_dfull, (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int d = 0; d <= OZ_DMAX; ++d) {
+          const int slot = d % 3;
+          const int64_t use = 2 * it + d / 3;      // how often this slot has been filled before
+          if (use >= 1) {
+            oz_mbar_wait(bar_sfree + 8 * slot, (uint32_t)((use - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t acc = tmem + (uint32_t)(slot * OZ_SLOT);
+          uint32_t first = 0;
+#pragma unroll 1
+          for (int i = 0; i <= d; ++i) {           // D slice i with operand slice j = d - i
+            const int j = d - i;
+            if (i >= OZ_NS || j >= OZ_NS) continue;
+            const uint32_t da = d_base + (uint32_t)(i * kc) * 2048;
+            const uint32_t ba = b_base + (uint32_t)j * b_plane;
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t a0 = da + (uint32_t)(2 * ks) * 2048;
+              const uint32_t b0 = ba + (uint32_t)(2 * ks) * ng * 128;
+              // second 16-byte K column of the step: the next column, or (odd column count)
+              // the zero block on the operand side, which cancels whatever the tile side reads
+              const bool tail = (2 * ks + 1 >= kc);
+              const uint64_t ad = oz_desc(a0, 2048, 128);
+              const uint64_t bd = oz_desc(b0, tail ? zero_base - b0 : (uint32_t)ng * 128, 128);
+              oz_mma(acc, ad, bd, idesc, first);
+              first = 1;
+            }
+          }
+          oz_commit(bar_sfull + 8 * slot);
+        }
+        oz_commit(bar_dfree);
+      }
+    }
+  } else {
+    // ====================== workers: produce the tile, then drain it ===================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+    const int m = tid & 127;             // real row of the tile: (det_local, part)
+    const int h = tid >> 7;              // K-column phase: columns h, h+4, h+8
+    const int det_local = m >> 1, part = m & 1;
+    const uint64_t *pos = p.planes + (int64_t)part * p.ndet;
+    const uint64_t *neg = p.planes + (int64_t)(2 + part) * p.ndet;
+    const uint64_t ZERO = 0x4040404040404040ull;
+    // epilogue geometry: lane quarter q (TMEM lanes 32q..32q+31) and column block cb
+    const int q = warp & 3, cblk = warp >> 2;
+    const int cpb = (p.np + 3) / 4;                 // columns per block (<= 36)
+    const int col0 = cblk * cpb;
+    const int erow = q * 32 + lane;                 // accumulator row handled in the epilogue
+    const double st = p.stats[2] * p.op_scale;      // S * T
+    double w[3];
+    {
+      const double r = 1.0 / (double)OZ_RADIX;
+      w[0] = st * r * r * r;                        // pair (d0,d1): R^-3 (acc0 R + acc1)
+      w[1] = w[0] * r * r;
+      w[2] = w[1] * r * r;
+    }
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int r = (int)(tile / p.tiles_per_row);
+      const int bt = (int)(tile - (int64_t)r * p.tiles_per_row);
+      const int64_t a = p.row0 + r;
+      // ---------------- produce ----------------
+      if (it >= 1) oz_mbar_wait(bar_dfree, (uint32_t)((it - 1) & 1));
+      {
+        const int64_t b = (int64_t)bt * OZ_TILE_DETS + det_local;
+        const bool valid = b < p.lenb;
+        const int32_t *ta_row = p.mapT_a + a * (int64_t)p.ntab;
+        const int32_t *mb = p.map_b + (valid ? b : 0);
+        const int64_t arow = a * p.lenb;
+        for (int g = h; g < kc; g += 4) {
+          uint32_t out[OZ_NS][4];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint64_t e[4];
+            int ta[4], tb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = 16 * g + 4 * qd + u;
+              const bool on = valid && k < p.np;
+              ta[u] = on ? oz_ldg32(ta_row + k) : 0;
+              tb[u] = on ? oz_ldg32(mb + (int64_t)k * p.lenb) : 0;
+            }
+            uint64_t va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              va[u] = ZERO;
+              vb[u] = ZERO;
+              if (ta[u] != 0)
+                va[u] = oz_ldg64((ta[u] > 0 ? pos : neg) + ((int64_t)(abs(ta[u]) - 1) * p.lenb + b));
+              if (tb[u] != 0)
+                vb[u] = oz_ldg64((tb[u] > 0 ? pos : neg) + (arow + (abs(tb[u]) - 1)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              e[u] = (va[u] + vb[u]) ^ 0x8080808080808080ull;   // signed digit sums, per byte
+            // 4 x 4 byte transposes: word s of `out` = slice s of the four k of this quad
+            const uint32_t l0 = (uint32_t)e[0], l1 = (uint32_t)e[1], l2 = (uint32_t)e[2],
+                           l3 = (uint32_t)e[3];
+            const uint32_t h0 = (uint32_t)(e[0] >> 32), h1 = (uint32_t)(e[1] >> 32),
+                           h2 = (uint32_t)(e[2] >> 32), h3 = (uint32_t)(e[3] >> 32);
+            const uint32_t t0 = __byte_perm(l0, l1, 0x5140), t1 = __byte_perm(l2, l3, 0x5140);
+            const uint32_t t2 = __byte_perm(l0, l1, 0x7362), t3 = __byte_perm(l2, l3, 0x7362);
+            out[0][qd] = __byte_perm(t0, t1, 0x5410);
+            out[1][qd] = __byte_perm(t0, t1, 0x7632);
+            out[2][qd] = __byte_perm(t2, t3, 0x5410);
+            out[3][qd] = __byte_perm(t2, t3, 0x7632);
+            const uint32_t t4 = __byte_perm(h0, h1, 0x5140), t5 = __byte_perm(h2, h3, 0x5140);
+            out[4][qd] = __byte_perm(t4, t5, 0x5410);
+            out[5][qd] = __byte_perm(t4, t5, 0x7632);
+          }
+          // 16-byte core-matrix rows: conflict-free (32 consecutive rows = 512 contiguous bytes)
+          const uint32_t dst = oz_smem_u32(s_d) + (uint32_t)(g * 16 + (m >> 3)) * 128 + (m & 7) * 16;
+#pragma unroll
+          for (int s = 0; s < OZ_NS; ++s)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)(s * kc) * 2048),
+                         "r"(out[s][0]), "r"(out[s][1]), "r"(out[s][2]), "r"(out[s][3])
+                         : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      oz_mbar_arrive(bar_dfull);
+      // ---------------- drain ----------------
+      double run[36];
+#pragma unroll
+      for (int c = 0; c < 36; ++c) run[c] = 0.0;
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        const int sa = (2 * pr) % 3, sb = (2 * pr + 1) % 3;
+        const int64_t ua = 2 * it + (2 * pr) / 3, ub = 2 * it + (2 * pr + 1) / 3;
+        oz_mbar_wait(bar_sfull + 8 * sa, (uint32_t)(ua & 1));
+        oz_mbar_wait(bar_sfull + 8 * sb, (uint32_t)(ub & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        // 36 columns per thread in rounds of 8, 8, 8, 8, 4 (small register footprint next to
+        // the 36 running sums)
+#pragma unroll
+        for (int rd = 0; rd < 5; ++rd) {
+          uint32_t ra[8], rb[8];
+          const uint32_t ca = tmem + lane_addr + (uint32_t)(sa * OZ_SLOT + col0 + 8 * rd);
+          const uint32_t cbb = tmem + lane_addr + (uint32_t)(sb * OZ_SLOT + col0 + 8 * rd);
+          if (rd < 4) {
+            OZ_TMEM_LD8(ra, ca);
+            OZ_TMEM_LD8(rb, cbb);
+          } else {
+            OZ_TMEM_LD4(ra, ca);
+            OZ_TMEM_LD4(rb, cbb);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < (rd < 4 ? 8 : 4); ++c) {
+            const int comb = (int)ra[c] * OZ_RADIX + (int)rb[c];
+            run[8 * rd + c] = fma(w[pr], (double)comb, run[8 * rd + c]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          oz_mbar_arrive(bar_sfree + 8 * sa);
+          oz_mbar_arrive(bar_sfree + 8 * sb);
+        }
+      }
+      // E[kl][r*pitch + b].{re,im}: row erow = (det, part); consecutive lanes -> consecutive doubles
+      {
+        const int edet = erow >> 1, epart = erow & 1;
+        const int64_t b = (int64_t)bt * OZ_TILE_DETS + edet;
+        if (b < p.lenb) {
+          double *base = reinterpret_cast<double *>(p.E + ((int64_t)r * p.pitch + b)) + epart;
+#pragma unroll
+          for (int c = 0; c < 36; ++c) {
+            const int kl = col0 + c;
+            if (c < cpb && kl < p.np) __stcs(base + 2 * (int64_t)kl * p.lde, run[c]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 16)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+constexpr int OZ_STATS_DOUBLES = 4 + 2 * 1024;
+// workspace bytes of the sliced path: digit planes + statistics block
+size_t ozaki_workspace_bytes(const fqeb_graph *g) {
+  return (size_t)round_up(sizeof(uint64_t) * 4 * (size_t)g->len[0] * g->len[1] + 64, 256) +
+         (size_t)round_up(sizeof(double) * OZ_STATS_DOUBLES, 256);
+}
+// the statistics block sits behind the planes
+double *ozaki_stats_ptr(const fqeb_graph *g, void *d_oz) {
+  return (double *)((char *)d_oz +
+                    round_up(sizeof(uint64_t) * 4 * (size_t)g->len[0] * g->len[1] + 64, 256));
+}
+
+// d_stats: device buffer of OZ_STATS_DOUBLES doubles.  Returns max |Re/Im C| and ||C||^2 on the
+// host (one small synchronising copy: the caller decides between this path and the DMMA path).
+int ozaki_stats(const fqeb_graph *g, const double *d_coeff, double *d_stats, double *h_absmax,
+                double *h_sumsq, cudaStream_t st) {
+  const int64_t ndet = g->len[0] * g->len[1];
+  const int nblocks = 1024;
+  k_absmax_sumsq<<<nblocks, 256, 0, st>>>(2 * ndet, d_coeff, d_stats + 4);
+  FQEB_CHECK_LAUNCH();
+  k_absmax_sumsq_final<<<1, 32, 0, st>>>(nblocks, d_stats + 4, d_stats);
+  FQEB_CHECK_LAUNCH();
+  double h[2];
+  FQEB_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  FQEB_CUDA(cudaStreamSynchronize(st));
+  *h_absmax = h[0];
+  *h_sumsq = h[1];
+  return FQEB_OK;
+}
+
+// digit planes of the coefficients (scale = d_stats[2], written by ozaki_stats)
+int ozaki_slice(const fqeb_graph *g, const double *d_coeff, const double *d_stats, void *d_planes,
+                cudaStream_t st) {
+  const int64_t ndet = g->len[0] * g->len[1];
+  int64_t blocks = (ndet + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  k_slice_coeff<<<(unsigned)blocks, 256, 0, st>>>(ndet, (const double2 *)d_coeff, d_stats,
+                                                   (uint64_t *)d_planes);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
+// estimated relative error of sigma from the global-scale quantisation of C
+double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq) {
+  if (!(sumsq > 0.0)) return 0.0;
+  const double ndet = (double)g->len[0] * (double)g->len[1];
+  double q = 2.0001 * absmax * 0.5 / sqrt(3.0);   // rms rounding error in units of the last digit
+  for (int i = 0; i < OZ_NS; ++i) q /= (double)OZ_RADIX;
+  return q * sqrt(2.0 * ndet) / sqrt(sumsq);
+}
+
+int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
+                 const double *d_stats, int64_t row0, int64_t nrows, int pitch, double *d_evec,
+                 int64_t lde, cudaStream_t st) {
+  FQEB_REQUIRE(ozaki_shape_ok(op), "ozaki: operator not supported by the sliced contraction");
+  FQEB_REQUIRE(pitch % OZ_TILE_DETS == 0 && pitch >= g->len[1] && lde >= nrows * (int64_t)pitch,
+               "ozaki: bad column layout");
+  OzOperand o;
+  int rc = ozaki_operand(op, g->nele[0] + g->nele[1], &o);
+  if (rc != FQEB_OK) return rc;
+  OzParams p;
+  p.img = o.d_img;
+  p.img_bytes = (int)o.img_bytes;
+  p.np = o.np;
+  p.kc = o.kc;
+  p.ng = o.ng;
+  p.n_mma = o.n_mma;
+  p.planes = (const uint64_t *)d_planes;
+  p.ndet = g->len[0] * g->len[1];
+  p.mapT_a = op->sym ? g->d_smapT[0] : g->d_amapT[0];
+  p.map_b = op->sym ? g->d_smap[1] : g->d_amap[1];
+  p.ntab = op->np;
+  p.lenb = g->len[1];
+  p.row0 = row0;
+  p.pitch = pitch;
+  p.tiles_per_row = pitch / OZ_TILE_DETS;
+  p.ntiles = nrows * p.tiles_per_row;
+  p.E = (double2 *)d_evec;
+  p.lde = lde;
+  p.stats = d_stats;
+  p.op_scale = o.scale;
+  // D^T tile + operand image (its zero block is also what the row groups past the pair space
+  // and the last slice's odd K column read)
+  const size_t smem = (size_t)OZ_NS * o.kc * 2048 + o.img_bytes;
+  FQEB_REQUIRE(smem <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    attr_set = true;
+  }
+  int64_t grid = sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  if (grid < 1) return FQEB_OK;
+  k_sigma_ozaki<<<(unsigned)grid, OZ_THREADS, smem, st>>>(p);
+  FQEB_CHECK_LAUNCH();
+  return FQEB_OK;
+}
+
+}  // namespace fqeb

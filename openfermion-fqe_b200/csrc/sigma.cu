@@ -48,6 +48,18 @@ int launch_contract(const fqeb_op *op, const double *d_A, const double *d_dvec, 
                     cudaStream_t st);
 int dvec_rows_padded(const fqeb_op *op, int nij);
 int dvec_rows_zeroed(const fqeb_op *op, int nij);
+// INT8-sliced tensor-core contraction (ozaki.cu)
+bool ozaki_shape_ok(const fqeb_op *op);
+size_t ozaki_workspace_bytes(const fqeb_graph *g);
+double *ozaki_stats_ptr(const fqeb_graph *g, void *d_oz);
+int ozaki_stats(const fqeb_graph *g, const double *d_coeff, double *d_stats, double *h_absmax,
+                double *h_sumsq, cudaStream_t st);
+int ozaki_slice(const fqeb_graph *g, const double *d_coeff, const double *d_stats, void *d_planes,
+                cudaStream_t st);
+double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq);
+int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
+                 const double *d_stats, int64_t row0, int64_t nrows, int pitch, double *d_evec,
+                 int64_t lde, cudaStream_t st);
 
 // ---- optional per-phase event timing ------------------------------------------------
 struct PhaseEvent {
@@ -79,8 +91,12 @@ struct PhaseTimer {
   }
 };
 
+static std::atomic<int> g_last_path{0};   // FQEB_PATH_* of the most recent two-body sigma build
+
 struct ChunkLayout {
-  bool fused;         // D never materialised (k_sigma_fused)
+  bool fused;         // D never materialised (k_sigma_fused / k_sigma_ozaki)
+  bool ozaki;         // the INT8-sliced contraction may be used: room for the digit planes
+  size_t oz_bytes;    // digit planes + statistics block, at the start of the workspace
   int64_t pitch;      // complex elements between consecutive alpha rows inside a D/E row
   int64_t ldd;        // complex elements per D / E row
   int64_t d_rows;     // rows of D (pair slice, padded); 0 when fused
@@ -98,10 +114,21 @@ static bool use_fused(const fqeb_graph *g, const fqeb_op *op) {
   return enabled && op->fuse_ok && (g->nele[0] + g->nele[1]) > 0;
 }
 
+// The sliced tensor-core contraction (ozaki.cu) replaces the DMMA stream of the fused kernel for
+// whole-pair-space builds of real / imaginary operators with a pair space <= 144 (FQEB_OZAKI=0
+// disables it); per call it is additionally gated on the state (see fqeb_sigma_restricted).
+static bool use_ozaki(const fqeb_graph *g, const fqeb_op *op, int ij0, int ij1) {
+  const char *env = getenv("FQEB_OZAKI");
+  const bool enabled = !(env && env[0] == '0');
+  return enabled && use_fused(g, op) && ozaki_shape_ok(op) && ij0 == 0 && ij1 == op->np;
+}
+
 static ChunkLayout layout_for(const fqeb_graph *g, const fqeb_op *op, int64_t rows, int ij0,
                               int ij1) {
   ChunkLayout L;
   L.fused = use_fused(g, op);
+  L.ozaki = use_ozaki(g, op, ij0, ij1);
+  L.oz_bytes = L.ozaki ? ozaki_workspace_bytes(g) : 0;
   L.e_rows = round_up(op->np, 8);
   if (L.fused) {
     L.pitch = round_up(g->len[1], 64);
@@ -137,7 +164,7 @@ extern "C" size_t fqeb_sigma_workspace_bytes(const fqeb_graph *g, const fqeb_op 
   if (check_shard(g, op, ij0, ij1) != FQEB_OK || rows_per_chunk <= 0) return 0;
   if (!op->has_h2 || ij0 == ij1) return 0;
   const ChunkLayout L = layout_for(g, op, rows_per_chunk, ij0, ij1);
-  return L.d_bytes + L.e_bytes;
+  return L.oz_bytes + L.d_bytes + L.e_bytes;
 }
 
 extern "C" int64_t fqeb_sigma_rows_for_workspace(const fqeb_graph *g, const fqeb_op *op,
@@ -190,19 +217,43 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
   const int64_t nchunk = (row1 - row0 + rows_chunk - 1) / rows_chunk;
   rows_chunk = (row1 - row0 + nchunk - 1) / nchunk;
   const ChunkLayout L = layout_for(g, op, rows_chunk, ij0, ij1);
-  double *d_dvec = (double *)d_workspace;
-  double *d_evec = (double *)((char *)d_workspace + L.d_bytes);
+  double *d_dvec = (double *)((char *)d_workspace + L.oz_bytes);
+  double *d_evec = (double *)((char *)d_workspace + L.oz_bytes + L.d_bytes);
   const int nij = ij1 - ij0;
   if (L.fused) {
+    // INT8-sliced tensor-core contraction, unless the state is too strongly peaked for a
+    // global fixed-point scale (estimated quantisation error above FQEB_OZAKI_TOL, default
+    // 5e-12 relative): then the FP64 DMMA kernel builds the same E.
+    bool sliced = L.ozaki;
+    double *d_stats = nullptr;
+    if (sliced) {
+      static const double tol = getenv("FQEB_OZAKI_TOL") ? atof(getenv("FQEB_OZAKI_TOL")) : 5e-12;
+      d_stats = ozaki_stats_ptr(g, d_workspace);
+      double absmax = 0.0, sumsq = 0.0;
+      PhaseTimer t(0, st);
+      rc = ozaki_stats(g, d_coeff, d_stats, &absmax, &sumsq, st);
+      if (rc != FQEB_OK) return rc;
+      if (!(sumsq > 0.0)) return FQEB_OK;   // zero vector: sigma is already zero
+      sliced = ozaki_error_estimate(g, absmax, sumsq) <= tol;
+      if (sliced) {
+        rc = ozaki_slice(g, d_coeff, d_stats, d_workspace, st);
+        if (rc != FQEB_OK) return rc;
+      }
+    }
+    g_last_path.store(sliced ? FQEB_PATH_SLICED : FQEB_PATH_FUSED);
     const double *d_A = nullptr;
-    rc = absorbed_operand(op, g->nele[0] + g->nele[1], &d_A);
-    if (rc != FQEB_OK) return rc;
-    double *d_e = (double *)d_workspace;
+    if (!sliced) {
+      rc = absorbed_operand(op, g->nele[0] + g->nele[1], &d_A);
+      if (rc != FQEB_OK) return rc;
+    }
+    double *d_e = d_evec;
     for (int64_t a0 = row0; a0 < row1; a0 += rows_chunk) {
       const int64_t nr = (row1 - a0) < rows_chunk ? (row1 - a0) : rows_chunk;
       {
         PhaseTimer t(1, st);
-        rc = launch_fused(g, op, d_A, d_coeff, a0, nr, (int)L.pitch, d_e, L.ldd, ij0, ij1, st);
+        rc = sliced ? launch_ozaki(g, op, d_workspace, d_stats, a0, nr, (int)L.pitch, d_e, L.ldd, st)
+                    : launch_fused(g, op, d_A, d_coeff, a0, nr, (int)L.pitch, d_e, L.ldd, ij0,
+                                   ij1, st);
       }
       if (rc != FQEB_OK) return rc;
       {
@@ -214,6 +265,7 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
     }
     return FQEB_OK;
   }
+  g_last_path.store(FQEB_PATH_THREE_KERNEL);
   const int zrows = dvec_rows_zeroed(op, nij);
   if (zrows > nij) {
     // the k-padding rows of D that a partial k4 step reads must be exact zeros
@@ -293,6 +345,8 @@ extern "C" int fqeb_taylor(const fqeb_graph *g, const fqeb_op *op, double *d_evo
   set_error("maximum taylor expansion limit reached (%d terms)", max_terms);
   return FQEB_ERR_CONVERGE;
 }
+
+extern "C" int fqeb_sigma_last_path(void) { return g_last_path.load(); }
 
 extern "C" int fqeb_profile_enable(int on) {
   std::lock_guard<std::mutex> lock(g_profile_mu);
