@@ -349,6 +349,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    path = int(lib.fqeb_sigma_last_path())
     checksum = float(torch.view_as_real(sigma).abs().sum().item())
     # the timed sigma against the reference's own result for these inputs (always on: it is
     # a few reductions on the device, outside the timed region)
@@ -365,59 +366,70 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         "ms_total": ms_max, "launches": int(launches),
         "phase_ms": [float(x) for x in ms3], "phase_launches": [int(x) for x in cnt3],
         "rows": rows, "pairs": pairs, "la": la, "lb": lb, "clocks": clocks,
-        "checksum": checksum, "verify": verify, "golden_verify": golden_verify,
+        "checksum": checksum, "verify": verify, "golden_verify": golden_verify, "path": path,
     }
 
     if do_e2e:
-        host_out = torch.empty((la, lb), dtype=torch.complex128).pin_memory()
+        from fqe_b200.distributed import ExchangeBuffers, HostApplyStream, SharedHostBuffer
+        # Host buffers.  One rank: pinned tensors.  Several ranks: pinned POSIX shared memory
+        # owned by rank 0 and mapped by every rank, so that rank 0's process holds the complete
+        # input and receives the complete sigma while every GPU moves only its block of rows.
+        shared = []
+        if world == 1:
+            host_in = host_c
+            outs = [torch.empty((la, lb), dtype=torch.complex128).pin_memory() for _ in range(2)]
+        else:
+            tag = "fqeb_%s_" % os.environ.get("MASTER_PORT", "0")
+            if rank == 0:
+                shared = [SharedHostBuffer(tag + nm, (la, lb), create=True)
+                          for nm in ("c", "s0", "s1")]
+                shared[0].tensor.copy_(host_c)
+            dist.barrier()
+            if rank != 0:
+                shared = [SharedHostBuffer(tag + nm, (la, lb)) for nm in ("c", "s0", "s1")]
+            host_in = shared[0].tensor
+            outs = [shared[1].tensor, shared[2].tensor]
+        bufs = ExchangeBuffers(sector, world, rank)
 
-        def e2e_step():
+        def e2e_step(k):
             ham = fqe.get_restricted_hamiltonian((h1, h2))
             op_i = wfn._dense_operator(ham.tensors())                # operator preparation
-            # H2D of this step's input (each rank its row slice, exchanged over NVLink),
-            # sharded sigma + allreduce, D2H of the result (each rank its row slice)
-            sharded_apply_host(sector, op_i, host_c, host_out, args.shard)
+            # H2D of this step's input (each rank its block of rows, completed by one all-gather
+            # over NVLink), sharded sigma, one reduce-scatter, D2H of each rank's block
+            sharded_apply_host(sector, op_i, host_in, outs[k % 2], args.shard, bufs)
             torch.cuda.synchronize()
 
-        e2e_step()
-        if args.verify:
-            ref = sharded_apply(sector, op, args.shard)
-            r0, r1 = (0, la) if world == 1 else __import__(
-                "fqe_b200.distributed", fromlist=["split_even"]).split_even(la, world)[rank]
-            got = host_out[r0:r1].cuda()
-            result["e2e_verify"] = float((torch.linalg.norm(got - ref[r0:r1]) /
-                                          torch.linalg.norm(ref[r0:r1])).item())
-            del ref, got
+        e2e_step(0)
+        barrier()
+        if rank == 0:   # the calling process holds the COMPLETE host sigma: check it
+            result["e2e_verify"] = verify_against_golden(outs[0].numpy(), norb, kind,
+                                                         numpy_state=True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        for k in range(args.steps):
+            e2e_step(k)
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         result["e2e_serial_s"] = float(t.item())
+        del bufs
         # the same K builds as a stream: upload of build k+1 / download of build k-1 overlap
         # build k on separate CUDA streams (every build still copies its own input and result)
-        from fqe_b200.distributed import HostApplyStream
-        host_out2 = torch.empty((la, lb), dtype=torch.complex128).pin_memory()
-        outs = [host_out, host_out2]
         pipe = HostApplyStream(sector, args.shard)
 
         def e2e_stream(k):
             ham = fqe.get_restricted_hamiltonian((h1, h2))
-            pipe.submit(wfn._dense_operator(ham.tensors()), host_c, outs[k % 2])
+            pipe.submit(wfn._dense_operator(ham.tensors()), host_in, outs[k % 2])
 
         for k in range(2):
             e2e_stream(k)
         pipe.drain()
-        if args.verify:
-            r0, r1 = (0, la) if world == 1 else __import__(
-                "fqe_b200.distributed", fromlist=["split_even"]).split_even(la, world)[rank]
+        barrier()
+        if rank == 0:
             result["e2e_stream_verify"] = float(
-                (torch.linalg.norm(host_out2[r0:r1] - host_out[r0:r1]) /
-                 torch.linalg.norm(host_out[r0:r1])).item())
+                (torch.linalg.norm(outs[1] - outs[0]) / torch.linalg.norm(outs[0])).item())
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
@@ -432,7 +444,31 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         del pipe
         # bytes over PCIe per step, summed over all ranks
         result["h2d"] = host_c.numel() * 16 + world * (h1.nbytes + h2.nbytes)
-        result["d2h"] = host_out.numel() * 16
+        result["d2h"] = outs[0].numel() * 16
+        # the reference-facing C-ABI call with plain (pageable) numpy buffers, one rank only:
+        # fqeb_sigma_restricted_host is what a maintainer binds at src/fqe/fqe_data.py:685
+        if world == 1:
+            import numpy as np
+            from fqe_b200.fqe_data import fold_restricted
+            h1p, h2p = fold_restricted(h1, h2)
+            c_np = np.array(host_c.numpy(), copy=True)          # pageable
+            s_np = np.empty_like(c_np)
+
+            def cabi_step():
+                rc = lib.fqeb_sigma_restricted_host(norb, na, nb, h1p.ctypes.data, h2p.ctypes.data,
+                                                    c_np.ctypes.data, s_np.ctypes.data)
+                if rc != 0:
+                    raise RuntimeError(lib.fqeb_last_error().decode())
+
+            cabi_step()
+            result["cabi_verify"] = verify_against_golden(s_np, norb, kind, numpy_state=True)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                cabi_step()
+            result["cabi_s"] = time.perf_counter() - t0
+        barrier()
+        for sh in shared:
+            sh.close()
     return result
 
 
@@ -525,17 +561,30 @@ def run_b200(args):
         "verify_rel_err": main["golden_verify"], "verify_against": "signature of the UNMODIFIED "
         "reference's sigma for these inputs (tests/golden/ref_large.npz)",
         "shard_verify_rel_err": main["verify"], "e2e_verify_rel_err": main.get("e2e_verify"),
+        "contraction_path": {0: "none", 1: "gather -> FP64 DMMA GEMM -> scatter",
+                             2: "gather fused into the FP64 DMMA contraction",
+                             3: "gather fused into the INT8-sliced tcgen05 contraction"}.get(
+            main.get("path"), None),
         "clocks": main["clocks"],
-        "e2e": {"value": args.steps / main["e2e_s"], "unit": "sigma/s",
+        "e2e": {"value": args.steps / main["e2e_serial_s"], "unit": "sigma/s",
                 "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
-                "mode": "K independent builds streamed through fqe_b200.distributed."
-                        "HostApplyStream: every build uploads its input from pinned host memory "
-                        "and downloads its result; upload of build k+1 and download of build "
-                        "k-1 overlap build k on separate CUDA streams",
-                "serial_value": args.steps / main["e2e_serial_s"],
-                "serial_mode": "same K builds one after the other (sharded_apply_host + "
-                               "synchronize per build, nothing overlapped)",
-                "stream_verify_rel_err": main.get("e2e_stream_verify")},
+                "mode": "K builds strictly one after the other through the public host-buffer API "
+                        "(fqe_b200.distributed.sharded_apply_host + synchronize per build): "
+                        "operator preparation, upload from pinned host memory, sigma, download; "
+                        "with N > 1 ranks the host arrays are pinned POSIX shared memory owned by "
+                        "rank 0, every rank moves its block of rows (one all-gather before, one "
+                        "reduce-scatter after the build) and rank 0 holds the complete host sigma",
+                "verify_rel_err": main.get("e2e_verify"),
+                "streamed_value": args.steps / main["e2e_s"],
+                "streamed_mode": "the same K builds software-pipelined (HostApplyStream): upload "
+                                 "of build k+1 and download of build k-1 overlap build k on "
+                                 "separate CUDA streams",
+                "stream_verify_rel_err": main.get("e2e_stream_verify"),
+                "cabi_host_value": (args.steps / main["cabi_s"]) if main.get("cabi_s") else None,
+                "cabi_host_mode": "fqeb_sigma_restricted_host through ctypes with plain pageable "
+                                  "numpy arrays in and out (the call INTEGRATION.md binds at "
+                                  "src/fqe/fqe_data.py:685), one GPU",
+                "cabi_host_verify_rel_err": main.get("cabi_verify")},
         "roofline": {
             "bound": "tensor",
             "kernel": ("k_sigma_fused (D tiles gathered into the shared-memory ring + FP64 DMMA "

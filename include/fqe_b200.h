@@ -183,10 +183,15 @@ int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
                           int64_t row0, int64_t row1, int ij0, int ij1,
                           void *stream);
 /* Same, HOST buffers in and out (the reference-facing call: numpy coeff in,
- * numpy sigma out); allocates and frees its own device memory, copies inside. */
+ * numpy sigma out; what a maintainer binds at src/fqe/fqe_data.py:685 in place of the three
+ * lm_apply_array12_* calls).  Pageable host memory is fine: transfers are staged through a
+ * pinned double buffer (host copy of block k+1 overlaps the DMA of block k).  Device copies of
+ * C and sigma, the workspace and the staging buffers are kept per device between calls
+ * (fqeb_host_release frees them); calls are serialised per process.  Synchronous.           */
 int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta,
                                const double *h_h1p, const double *h_h2p,
                                const double *h_coeff, double *h_sigma);
+int fqeb_host_release(void);
 
 /* Which contraction path the most recent two-body fqeb_sigma_restricted call took (a test /
  * benchmark aid; the result is the same sigma to the tolerance of the path):

@@ -52,6 +52,8 @@ constexpr int OZ_SLOT = 144;       // TMEM columns per accumulator slot
 constexpr int OZ_WORKERS = 512;    // 16 worker warps: producers, then epilogue
 constexpr int OZ_THREADS = OZ_WORKERS + 128;   // + one warpgroup: MMA issuer (3 warps idle)
 constexpr int OZ_TILE_DETS = 64;   // determinants per tile (128 real rows)
+constexpr int OZ_NPROD = (OZ_DMAX + 1) * (OZ_DMAX + 2) / 2;   // 21 slice products
+constexpr int OZ_MAX_MMAS = OZ_NPROD * 5;                     // x K steps (<= 5)
 
 // ---------------------------------------------------------------------------------------
 // coefficient digit planes
@@ -351,9 +353,13 @@ struct OzParams {
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar[8];
   __shared__ uint32_t s_tmem;
+  // (A descriptor, B descriptor) of every MMA of a tile, in issue order: loop-invariant, so the
+  // single issuing thread only loads 16 bytes and fires (a dependent ALU chain per MMA was
+  // measured at 175 cycles per MMA, 2.4x the 72-cycle tensor time of a 128 x 144 x 32 step)
+  __shared__ __align__(16) uint4 s_desc[OZ_MAX_MMAS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kc = p.kc, ng = p.ng;
   const uint32_t d_bytes = (uint32_t)OZ_NS * kc * 2048;   // D^T tile: [slice][kcol][16 groups][128]
@@ -376,6 +382,30 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       oz_mbar_init(bar_sfree + 8 * s, OZ_WORKERS / 32);
     }
   }
+  {
+    const uint32_t d_base = oz_smem_u32(s_d), b_base = oz_smem_u32(s_b);
+    const uint32_t b_plane = (uint32_t)kc * ng * 128;
+    const uint32_t zero_base = b_base + OZ_NS * b_plane;
+    const int ksteps = (kc + 1) / 2;
+    for (int e = tid; e < OZ_NPROD * ksteps; e += OZ_THREADS) {
+      // entry e = (product pr, K step ks); products ordered by diagonal d = i + j, then i
+      const int pr = e / ksteps, ks = e - pr * ksteps;
+      int d = 0, rem = pr;
+      while (rem > d) {
+        rem -= d + 1;
+        ++d;
+      }
+      const int i = rem, j = d - rem;   // D slice i, operand slice j
+      const uint32_t a0 = d_base + (uint32_t)(i * kc + 2 * ks) * 2048;
+      const uint32_t b0 = b_base + (uint32_t)j * b_plane + (uint32_t)(2 * ks) * ng * 128;
+      // second 16-byte K column of the step: the next column, or (odd column count) the zero
+      // block on the operand side, which cancels whatever the tile side reads there
+      const bool tail = (2 * ks + 1 >= kc);
+      const uint64_t ad = oz_desc(a0, 2048, 128);
+      const uint64_t bd = oz_desc(b0, tail ? zero_base - b0 : (uint32_t)ng * 128, 128);
+      s_desc[e] = make_uint4((uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32));
+    }
+  }
   if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         oz_smem_u32(&s_tmem)));
@@ -393,17 +423,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
     // ================================ MMA issuer ======================================
     // this warpgroup hands its registers to the workers (5 warps per scheduler at launch
     // leave 96 registers per thread; the workers need ~110 for 36 running FP64 sums)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
     if (warp == 16 && lane == 0) {
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
-      const uint32_t d_base = oz_smem_u32(s_d), b_base = oz_smem_u32(s_b);
-      const uint32_t b_plane = (uint32_t)kc * ng * 128;
-      const uint32_t zero_base = b_base + OZ_NS * b_plane;
       const int ksteps = (kc + 1) / 2;
       for (int64_t it = 0; it < my_tiles; ++it) {
         oz_mbar_wait(bar_dfull, (uint32_t)(it & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int e = 0;
 #pragma unroll 1
         for (int d = 0; d <= OZ_DMAX; ++d) {
           const int slot = d % 3;
@@ -413,25 +441,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           const uint32_t acc = tmem + (uint32_t)(slot * OZ_SLOT);
+          const int e_end = e + (d + 1) * ksteps;
+          uint4 cur = s_desc[e];
           uint32_t first = 0;
 #pragma unroll 1
-          for (int i = 0; i <= d; ++i) {           // D slice i with operand slice j = d - i
-            const int j = d - i;
-            if (i >= OZ_NS || j >= OZ_NS) continue;
-            const uint32_t da = d_base + (uint32_t)(i * kc) * 2048;
-            const uint32_t ba = b_base + (uint32_t)j * b_plane;
-#pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t a0 = da + (uint32_t)(2 * ks) * 2048;
-              const uint32_t b0 = ba + (uint32_t)(2 * ks) * ng * 128;
-              // second 16-byte K column of the step: the next column, or (odd column count)
-              // the zero block on the operand side, which cancels whatever the tile side reads
-              const bool tail = (2 * ks + 1 >= kc);
-              const uint64_t ad = oz_desc(a0, 2048, 128);
-              const uint64_t bd = oz_desc(b0, tail ? zero_base - b0 : (uint32_t)ng * 128, 128);
-              oz_mma(acc, ad, bd, idesc, first);
-              first = 1;
-            }
+          for (; e < e_end; ++e) {
+            const uint4 nxt = s_desc[e + 1 < OZ_MAX_MMAS ? e + 1 : e];   // prefetch
+            oz_mma(acc, (uint64_t)cur.x | ((uint64_t)cur.y << 32),
+                   (uint64_t)cur.z | ((uint64_t)cur.w << 32), idesc, first);
+            first = 1;
+            cur = nxt;
           }
           oz_commit(bar_sfull + 8 * slot);
         }
@@ -674,12 +693,12 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   // D^T tile + operand image (its zero block is also what the row groups past the pair space
   // and the last slice's odd K column read)
   const size_t smem = (size_t)OZ_NS * o.kc * 2048 + o.img_bytes;
-  FQEB_REQUIRE(smem <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  FQEB_REQUIRE(smem + 1856 <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
+  static size_t attr_bytes = 0;   // dynamic + static shared memory must stay within 227 KB
+  if (smem > attr_bytes) {
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
-    attr_set = true;
+                                   (int)smem));
+    attr_bytes = smem;
   }
   int64_t grid = sm_count();
   if (grid > p.ntiles) grid = p.ntiles;

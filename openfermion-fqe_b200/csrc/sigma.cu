@@ -23,8 +23,10 @@
 // sigma that one allreduce completes.
 #include "fqeb_common.cuh"
 
+#include <string.h>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -397,6 +399,146 @@ fqeb_graph *cached_graph(int norb, int na, int nb, int *rc) {
 }
 }  // namespace
 
+namespace {
+// Per-device context of the host-buffer entry point: device copies of C and sigma, the D/E
+// workspace and a pinned double buffer for the transfers are allocated once and reused, so
+// that a caller looping over fqeb_sigma_restricted_host (a Taylor series driven from the
+// reference's Python) pays for allocation and page pinning once.
+struct HostCtx {
+  double *d_c = nullptr, *d_s = nullptr;
+  size_t cbytes = 0;
+  void *d_ws = nullptr;
+  size_t ws_bytes = 0;
+  char *h_stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+std::map<int, HostCtx> g_host_ctx;
+std::mutex g_host_mu;   // the entry point is serialised per process (one workspace per device)
+
+void parallel_memcpy(char *dst, const char *src, size_t n) {
+  const size_t kMin = 8u << 20;
+  unsigned nt = n >= 4 * kMin ? 4 : (n >= 2 * kMin ? 2 : 1);
+  if (nt == 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (n / nt + 63) & ~(size_t)63;
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t lo = (size_t)t * per, hi = (t + 1 == nt) ? n : ((size_t)(t + 1) * per < n ? (size_t)(t + 1) * per : n);
+    if (lo >= hi) break;
+    pool.emplace_back([=]() { memcpy(dst + lo, src + lo, hi - lo); });
+  }
+  for (auto &th : pool) th.join();
+}
+
+// pageable host -> device through the pinned double buffer: the host-side copy of block k+1
+// overlaps the DMA of block k
+int staged_upload(HostCtx &c, void *d_dst, const void *h_src, size_t bytes) {
+  bool used[2] = {false, false};
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += c.stage_bytes, ++k) {
+    const int slot = k & 1;
+    const size_t n = bytes - off < c.stage_bytes ? bytes - off : c.stage_bytes;
+    if (used[slot]) FQEB_CUDA(cudaEventSynchronize(c.ev[slot]));
+    parallel_memcpy(c.h_stage[slot], (const char *)h_src + off, n);
+    FQEB_CUDA(cudaMemcpyAsync((char *)d_dst + off, c.h_stage[slot], n, cudaMemcpyHostToDevice, c.st));
+    FQEB_CUDA(cudaEventRecord(c.ev[slot], c.st));
+    used[slot] = true;
+  }
+  return FQEB_OK;
+}
+
+int staged_download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes) {
+  size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+  bool used[2] = {false, false};
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += c.stage_bytes, ++k) {
+    const int slot = k & 1;
+    const size_t n = bytes - off < c.stage_bytes ? bytes - off : c.stage_bytes;
+    if (used[slot]) {   // drain the block that still sits in this slot
+      FQEB_CUDA(cudaEventSynchronize(c.ev[slot]));
+      parallel_memcpy((char *)h_dst + pend_off[slot], c.h_stage[slot], pend_n[slot]);
+    }
+    FQEB_CUDA(cudaMemcpyAsync(c.h_stage[slot], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, c.st));
+    FQEB_CUDA(cudaEventRecord(c.ev[slot], c.st));
+    pend_off[slot] = off;
+    pend_n[slot] = n;
+    used[slot] = true;
+  }
+  for (int j = 0; j < 2; ++j) {   // oldest first
+    const int slot = (k + j) & 1;
+    if (used[slot]) {
+      FQEB_CUDA(cudaEventSynchronize(c.ev[slot]));
+      parallel_memcpy((char *)h_dst + pend_off[slot], c.h_stage[slot], pend_n[slot]);
+      used[slot] = false;
+    }
+  }
+  return FQEB_OK;
+}
+
+int host_ctx_prepare(HostCtx &c, const fqeb_graph *g, const fqeb_op *op) {
+  const size_t cbytes = sizeof(double) * 2 * (size_t)g->len[0] * g->len[1];
+  if (!c.st) {
+    FQEB_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j) FQEB_CUDA(cudaEventCreateWithFlags(&c.ev[j], cudaEventDisableTiming));
+    c.stage_bytes = 64u << 20;
+    for (int j = 0; j < 2; ++j) FQEB_CUDA(cudaMallocHost((void **)&c.h_stage[j], c.stage_bytes));
+  }
+  if (cbytes > c.cbytes) {
+    if (c.d_c) cudaFree(c.d_c);
+    if (c.d_s) cudaFree(c.d_s);
+    c.d_c = c.d_s = nullptr;
+    c.cbytes = 0;
+    if (cudaMalloc(&c.d_c, cbytes) != cudaSuccess || cudaMalloc(&c.d_s, cbytes) != cudaSuccess) {
+      set_error("sigma_host: cannot allocate coefficient buffers (%zu bytes each)", cbytes);
+      return FQEB_ERR_NOMEM;
+    }
+    c.cbytes = cbytes;
+  }
+  if (op->has_h2) {
+    const size_t want = fqeb_sigma_workspace_bytes(g, op, g->len[0], 0, op->np);
+    if (want > c.ws_bytes) {
+      if (c.d_ws) cudaFree(c.d_ws);
+      c.d_ws = nullptr;
+      c.ws_bytes = 0;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const size_t budget = (size_t)(0.85 * (double)free_b);
+      const size_t take = want < budget ? want : budget;
+      if (cudaMalloc(&c.d_ws, take) != cudaSuccess) {
+        set_error("sigma_host: cannot allocate %zu-byte workspace", take);
+        return FQEB_ERR_NOMEM;
+      }
+      c.ws_bytes = take;
+    }
+  }
+  return FQEB_OK;
+}
+}  // namespace
+
+// release everything fqeb_sigma_restricted_host keeps between calls (all devices)
+extern "C" int fqeb_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  for (auto &kv : g_host_ctx) {
+    HostCtx &c = kv.second;
+    cudaSetDevice(kv.first);
+    if (c.st) cudaStreamSynchronize(c.st);
+    if (c.d_c) cudaFree(c.d_c);
+    if (c.d_s) cudaFree(c.d_s);
+    if (c.d_ws) cudaFree(c.d_ws);
+    for (int j = 0; j < 2; ++j) {
+      if (c.h_stage[j]) cudaFreeHost(c.h_stage[j]);
+      if (c.ev[j]) cudaEventDestroy(c.ev[j]);
+    }
+    if (c.st) cudaStreamDestroy(c.st);
+  }
+  g_host_ctx.clear();
+  return FQEB_OK;
+}
+
 extern "C" int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta, const double *h_h1p,
                                           const double *h_h2p, const double *h_coeff,
                                           double *h_sigma) {
@@ -408,48 +550,21 @@ extern "C" int fqeb_sigma_restricted_host(int norb, int nalpha, int nbeta, const
   fqeb_op *op = nullptr;
   rc = fqeb_op_create(norb, h_h1p, h_h2p, &op);
   if (rc != FQEB_OK) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  HostCtx &c = g_host_ctx[dev];
+  rc = host_ctx_prepare(c, g, op);
   const size_t cbytes = sizeof(double) * 2 * (size_t)g->len[0] * g->len[1];
-  double *d_c = nullptr, *d_s = nullptr;
-  void *d_ws = nullptr;
-  size_t ws_bytes = 0;
-  auto cleanup = [&]() {
-    if (d_c) cudaFree(d_c);
-    if (d_s) cudaFree(d_s);
-    if (d_ws) cudaFree(d_ws);
-    fqeb_op_destroy(op);
-  };
-  const int npair = op->np;
-  if (cudaMalloc(&d_c, cbytes) != cudaSuccess || cudaMalloc(&d_s, cbytes) != cudaSuccess) {
-    set_error("sigma_host: cannot allocate coefficient buffers (%zu bytes each)", cbytes);
-    cleanup();
-    return FQEB_ERR_NOMEM;
+  if (rc == FQEB_OK) rc = staged_upload(c, c.d_c, h_coeff, cbytes);
+  if (rc == FQEB_OK)
+    rc = fqeb_sigma_restricted(g, op, c.d_c, c.d_s, c.d_ws, c.ws_bytes, 0, g->len[0], 0, op->np,
+                               c.st);
+  if (rc == FQEB_OK) rc = staged_download(c, h_sigma, c.d_s, cbytes);
+  if (rc == FQEB_OK && cudaStreamSynchronize(c.st) != cudaSuccess) {
+    set_error("sigma_host: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = FQEB_ERR_CUDA;
   }
-  if (op->has_h2) {
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    const size_t want = fqeb_sigma_workspace_bytes(g, op, g->len[0], 0, npair);
-    size_t budget = (size_t)(0.85 * (double)free_b);
-    ws_bytes = want < budget ? want : budget;
-    if (cudaMalloc(&d_ws, ws_bytes) != cudaSuccess) {
-      set_error("sigma_host: cannot allocate %zu-byte workspace", ws_bytes);
-      cleanup();
-      return FQEB_ERR_NOMEM;
-    }
-  }
-  cudaError_t e = cudaMemcpy(d_c, h_coeff, cbytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    rc = fqeb_sigma_restricted(g, op, d_c, d_s, d_ws, ws_bytes, 0, g->len[0], 0, npair, nullptr);
-    if (rc != FQEB_OK) {
-      cleanup();
-      return rc;
-    }
-    e = cudaMemcpy(h_sigma, d_s, cbytes, cudaMemcpyDeviceToHost);
-  }
-  if (e != cudaSuccess) {
-    set_error("sigma_host: copy failed: %s", cudaGetErrorString(e));
-    cleanup();
-    return FQEB_ERR_CUDA;
-  }
-  cleanup();
-  return FQEB_OK;
+  fqeb_op_destroy_async(op, c.st);
+  return rc;
 }

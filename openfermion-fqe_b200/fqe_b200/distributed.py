@@ -68,32 +68,108 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
     return allreduce_sigma(part)
 
 
-def sharded_apply_host(sector, op, host_coeff: torch.Tensor, host_sigma: torch.Tensor,
-                       mode: str = "det") -> None:
-    """End-to-end sigma with HOST buffers on every rank.
+def block_slices(total: int, world: int) -> List[Tuple[int, int]]:
+    """Equal blocks of ceil(total / world) rows (the last ones shorter or empty): the layout of
+    one all-gather / reduce-scatter over a buffer padded to world * ceil(total / world) rows."""
+    per = (total + world - 1) // world
+    return [(min(total, r * per), min(total, (r + 1) * per)) for r in range(world)]
 
-    Each rank uploads only its 1/world row slice of ``host_coeff`` (pinned), the slices
-    are exchanged over NVLink (one broadcast per owner) so that every GPU holds the full
-    coefficient matrix, the sharded sigma build and its all-reduce run on the devices,
-    and each rank downloads its row slice of the result into ``host_sigma``.  Host <->
-    device traffic per rank is 2 * 16 * L^2 / world bytes instead of 2 * 16 * L^2."""
+
+class ExchangeBuffers:
+    """Device storage of one sector for the host-buffer path on ``world`` ranks: coefficient and
+    sigma matrices padded to ``world * ceil(lena / world)`` rows, so that the coefficient
+    exchange is ONE in-place ``all_gather_into_tensor`` and the reduction of the partial sigmas
+    ONE ``reduce_scatter_tensor`` (each rank only needs the rows it sends home)."""
+
+    def __init__(self, sector, world: int, rank: int):
+        from fqe_b200.fqe_data import FqeData
+        self.world, self.rank = world, rank
+        lena, lenb = sector.lena(), sector.lenb()
+        self.per = (lena + world - 1) // world
+        self.slices = block_slices(lena, world)
+        dev = sector.coeff.device
+        self.cstore = torch.zeros((world * self.per, lenb), dtype=torch.complex128, device=dev)
+        self.sstore = torch.empty((world * self.per, lenb), dtype=torch.complex128, device=dev)
+        self.mine = torch.empty((self.per, lenb), dtype=torch.complex128, device=dev)
+        self.data = FqeData(sector.nalpha(), sector.nbeta(), sector.norb(), sector.get_fcigraph())
+        self.data.coeff = self.cstore[:lena]          # a contiguous prefix: no copy
+
+    def gather_coeff(self) -> None:
+        """every rank has written its block of ``cstore``; afterwards all ranks hold all blocks"""
+        if self.world == 1:
+            return
+        r = self.rank
+        dist.all_gather_into_tensor(torch.view_as_real(self.cstore),
+                                    torch.view_as_real(self.cstore[r * self.per:(r + 1) * self.per]))
+
+    def build(self, op, mode: str) -> torch.Tensor:
+        """partial sigma of this rank's shard into ``sstore``; returns this rank's block of the
+        SUM over ranks (rows ``slices[rank]``)"""
+        lena = self.data.lena()
+        rows, pairs = shard_plan(mode, self.rank, self.world, lena, op.npair)
+        self.data.apply_operator(op, row_range=rows, pair_range=pairs, out=self.sstore[:lena])
+        if self.world == 1:
+            return self.sstore[:lena]
+        if self.world * self.per > lena:
+            self.sstore[lena:].zero_()
+        dist.reduce_scatter_tensor(torch.view_as_real(self.mine), torch.view_as_real(self.sstore))
+        r0, r1 = self.slices[self.rank]
+        return self.mine[:r1 - r0]
+
+
+def sharded_apply_host(sector, op, host_coeff: torch.Tensor, host_sigma: torch.Tensor,
+                       mode: str = "det", buffers: "ExchangeBuffers" = None) -> None:
+    """End-to-end sigma with HOST buffers.
+
+    Every rank uploads its block of rows of ``host_coeff`` (pinned), ONE all-gather over NVLink
+    completes the coefficient matrix on every GPU, the sharded sigma build runs, ONE
+    reduce-scatter leaves on every rank the rows it is responsible for, and each rank
+    downloads those rows into ``host_sigma``.  Host <-> device traffic per rank is
+    2 * 16 * L^2 / world bytes.  With ``SharedHostBuffer`` arrays for ``host_coeff`` /
+    ``host_sigma`` the caller's process (rank 0) ends up holding the complete host sigma while
+    the PCIe traffic is spread over all GPUs."""
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-    if world == 1:
-        sector.coeff.copy_(host_coeff, non_blocking=True)
-        sigma = sector.apply_operator(op)
-        host_sigma.copy_(sigma, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return
-    rank = dist.get_rank()
-    slices = split_even(sector.lena(), world)
-    r0, r1 = slices[rank]
-    sector.coeff[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
-    for src, (s0, s1) in enumerate(slices):
-        if s1 > s0:
-            dist.broadcast(torch.view_as_real(sector.coeff[s0:s1]), src=src)
-    sigma = sharded_apply(sector, op, mode)
-    host_sigma[r0:r1].copy_(sigma[r0:r1], non_blocking=True)
+    rank = dist.get_rank() if world > 1 else 0
+    if buffers is None:
+        buffers = ExchangeBuffers(sector, world, rank)
+    r0, r1 = buffers.slices[rank]
+    if r1 > r0:
+        buffers.cstore[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
+    buffers.gather_coeff()
+    mine = buffers.build(op, mode)
+    if r1 > r0:
+        host_sigma[r0:r1].copy_(mine, non_blocking=True)
     torch.cuda.current_stream().synchronize()
+
+
+class SharedHostBuffer:
+    """A pinned host array in POSIX shared memory that every rank of the node maps: rank 0 owns
+    the data (``numpy in, numpy out`` for the calling process), the other ranks read / write
+    their row blocks directly, so host <-> device copies run on all PCIe links at once."""
+
+    def __init__(self, name: str, shape, dtype=torch.complex128, create: bool = False):
+        import numpy
+        import os
+        self.path = os.path.join("/dev/shm", name)
+        nbytes = int(numpy.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if create:
+            with open(self.path, "wb") as fh:
+                fh.truncate(nbytes)
+        self._map = numpy.memmap(self.path, dtype=numpy.uint8, mode="r+", shape=(nbytes,))
+        self.tensor = torch.from_numpy(self._map).view(dtype).reshape(shape)
+        self._registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+            self._registered = int(rc) == 0
+        self._owner = create
+
+    def close(self) -> None:
+        import os
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        if self._owner and os.path.exists(self.path):
+            os.unlink(self.path)
 
 
 class HostApplyStream:
@@ -107,56 +183,52 @@ class HostApplyStream:
             pipe.submit(op, c_host, s_host)
         pipe.drain()                            # all results have landed in their s_host
 
-    With more than one rank each rank uploads / downloads only its row slice (as
-    ``sharded_apply_host``); the exchange and the all-reduce stay on the compute stream."""
+    With more than one rank each rank uploads / downloads only its block of rows (as
+    ``sharded_apply_host``); the all-gather and the reduce-scatter stay on the compute stream."""
 
     def __init__(self, sector, mode: str = "det", depth: int = 2):
-        from fqe_b200.fqe_data import FqeData
         self.mode = mode
         self.world = dist.get_world_size() if (dist.is_available() and
                                                dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        self.slices = split_even(sector.lena(), self.world)
         self.s_in = torch.cuda.Stream()
         self.s_out = torch.cuda.Stream()
         self.slots = []
         for _ in range(depth):
-            data = FqeData(sector.nalpha(), sector.nbeta(), sector.norb(), sector.get_fcigraph())
-            self.slots.append({"data": data, "sigma": None, "h2d": torch.cuda.Event(),
-                               "done": torch.cuda.Event(), "d2h": torch.cuda.Event(),
-                               "used": False})
+            self.slots.append({"buf": ExchangeBuffers(sector, self.world, self.rank),
+                               "h2d": torch.cuda.Event(), "done": torch.cuda.Event(),
+                               "d2h": torch.cuda.Event(), "used": False})
+        # the slots were initialised on the current stream: order the first uploads after that
+        self.s_in.wait_stream(torch.cuda.current_stream())
+        self.s_out.wait_stream(torch.cuda.current_stream())
         self.count = 0
 
     def submit(self, op, host_coeff: torch.Tensor, host_sigma: torch.Tensor) -> None:
         slot = self.slots[self.count % len(self.slots)]
         self.count += 1
         cur = torch.cuda.current_stream()
-        r0, r1 = self.slices[self.rank]
-        data = slot["data"]
+        buf = slot["buf"]
+        r0, r1 = buf.slices[self.rank]
         if slot["used"]:
             slot["d2h"].synchronize()          # the result that lived in this slot is home
             self.s_in.wait_event(slot["done"])  # and its coefficients are no longer read
         with torch.cuda.stream(self.s_in):
-            data.coeff[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
+            if r1 > r0:
+                buf.cstore[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
             slot["h2d"].record(self.s_in)
         cur.wait_event(slot["h2d"])
-        if self.world > 1:
-            for src, (s0, s1) in enumerate(self.slices):
-                if s1 > s0:
-                    dist.broadcast(torch.view_as_real(data.coeff[s0:s1]), src=src)
-        sigma = sharded_apply(data, op, self.mode)
+        buf.gather_coeff()
+        mine = buf.build(op, self.mode)
         slot["done"].record(cur)
-        sigma.record_stream(self.s_out)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["done"])
-            host_sigma[r0:r1].copy_(sigma[r0:r1], non_blocking=True)
+            if r1 > r0:
+                host_sigma[r0:r1].copy_(mine, non_blocking=True)
             slot["d2h"].record(self.s_out)
-        slot["sigma"] = sigma
         slot["used"] = True
 
     def drain(self) -> None:
         for slot in self.slots:
             if slot["used"]:
                 slot["d2h"].synchronize()
-                slot["sigma"] = None
         torch.cuda.current_stream().synchronize()

@@ -108,6 +108,16 @@ def release_workspace() -> None:
 # ---------------------------------------------------------------------------
 # prepared dense operator
 # ---------------------------------------------------------------------------
+def fold_restricted(h1e: numpy.ndarray, h2e: numpy.ndarray) -> Tuple[numpy.ndarray, numpy.ndarray]:
+    """Tensor preparation of FqeData._apply_array_spatial12_lm (reference fqe_data.py:691-693):
+    h2' = -moveaxis(h2, 1, 2), h1' = h1 - sum_k h2'[i,k,k,j]; complex128, C-contiguous - the
+    arguments ``fqeb_op_create`` and ``fqeb_sigma_restricted_host`` take."""
+    h2p = numpy.ascontiguousarray(-numpy.moveaxis(numpy.asarray(h2e).astype(_C128), 1, 2))
+    h1p = numpy.ascontiguousarray(numpy.asarray(h1e).astype(_C128) -
+                                  numpy.einsum("ikkj->ij", h2p))
+    return h1p, h2p
+
+
 class DenseOperator:
     """(h1, h2) folded and uploaded for repeated sigma builds.
 
@@ -414,15 +424,22 @@ class FqeData:
         else:
             raise NotImplementedError("4-body dense operators are outside the B200 hot path")
 
-    def apply_operator(self, op: DenseOperator, row_range=None, pair_range=None) -> torch.Tensor:
+    def apply_operator(self, op: DenseOperator, row_range=None, pair_range=None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """sigma for a prepared operator.  ``row_range`` / ``pair_range`` restrict the
-        work to one rank's shard (partial sigma)."""
+        work to one rank's shard (partial sigma); ``out`` is an optional caller-owned
+        contiguous complex128 [lena, lenb] CUDA tensor that receives the result."""
         dev = _require_cuda()
         if op.norb != self.norb():
             raise ValueError("operator / wavefunction orbital mismatch")
         r0, r1 = row_range if row_range is not None else (0, self.lena())
         p0, p1 = pair_range if pair_range is not None else (0, op.npair)
-        sigma = torch.empty_like(self.coeff)
+        if out is None:
+            sigma = torch.empty_like(self.coeff)
+        else:
+            if tuple(out.shape) != tuple(self.coeff.shape):
+                raise ValueError("out has the wrong shape")
+            sigma = self._check_coeff(out)
         ws_ptr, ws_bytes = None, 0
         if op.has_h2 and r1 > r0 and p1 > p0:
             lib = _lib.load()

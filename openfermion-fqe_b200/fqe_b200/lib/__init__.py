@@ -35,6 +35,7 @@ SIGNATURES = {
     "fqeb_device_count": (c_int, []),
     "fqeb_launch_count": (c_uint64, []),
     "fqeb_sigma_last_path": (c_int, []),
+    "fqeb_host_release": (c_int, []),
     "fqeb_set_device": (c_int, [c_int]),
     "fqeb_graph_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
     "fqeb_graph_destroy": (c_int, [c_void_p]),

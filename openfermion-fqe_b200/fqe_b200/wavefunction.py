@@ -460,21 +460,30 @@ class Wavefunction:
         return out
 
     def save(self, filename: str, path: str = os.getcwd()) -> None:
-        """Pickle [conserved, norb, [key, complex128 ndarray]...] (own format: the reference
-        pickles its FqeData objects, which only the reference package can load)."""
-        data = [dict(self._conserved), self._norb]
-        for key, sec in self._civec.items():
-            data.append([key, sec.to_numpy()])
+        """Write path/filename in the reference's own file layout
+        (wavefunction.py:743-765: [symmetry_map, conserved, conserve_spin, conserve_number, norb,
+        [key, FqeData]...]); the sector entries re-create ``fqe.fqe_data.FqeData`` objects when
+        the file is read where the reference is installed (fqe_b200/wfn_io.py)."""
+        from fqe_b200 import wfn_io
+        sectors = {key: (sec.nalpha(), sec.nbeta(), sec.to_numpy())
+                   for key, sec in self._civec.items()}
         with open(os.path.join(path, filename), 'w+b') as fh:
-            pickle.dump(data, fh)
+            wfn_io.dump(fh, self._conserved, self._norb, sectors, self._conserve_spin,
+                        self._conserve_number)
 
     def read(self, filename: str, path: str = os.getcwd()) -> None:
+        """Initialise from a file written by this package OR by the reference's
+        ``Wavefunction.save`` (wavefunction.py:726-741).  Nothing but numpy arrays is ever
+        un-pickled: classes of the reference package are mapped to attribute bags."""
+        from fqe_b200 import wfn_io
         with open(os.path.join(path, filename), 'r+b') as fh:
-            data = pickle.load(fh)
-        self._conserved, self._norb = dict(data[0]), data[1]
+            data = wfn_io.load(fh)
+        if not (data["conserve_spin"] and data["conserve_number"]):
+            raise NotImplementedError("number- or spin-broken wavefunctions are outside the "
+                                      "B200 hot path")
+        self._conserved, self._norb = dict(data["conserved"]), data["norb"]
         self._civec = {}
-        for key, arr in data[2:]:
-            nele, m_s = key
+        for (nele, m_s), arr in data["sectors"].items():
             na, nb = alpha_beta_electrons(nele, m_s)
             sec = FqeData(na, nb, self._norb)
             sec.set_wfn(strategy='from_data', raw_data=arr)

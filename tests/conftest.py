@@ -49,3 +49,32 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+# ---------------------------------------------------------------------------------------------
+# Two contraction back ends build the same sigma: the INT8-sliced tensor-core kernel (default
+# where it applies; digits quantised at 127^-6, measured ~1e-12 relative) and the FP64 DMMA
+# kernels (FQEB_OZAKI=0; ~1e-15).  Modules that exercise sigma use the ``contraction`` fixture to
+# run on both, each held to its own bound; both are far inside the 1e-10 of BASELINE.json.
+# ---------------------------------------------------------------------------------------------
+SLICED_TOL = 2.0e-11
+FP64_TOL = 1.0e-12
+
+
+def sigma_tol() -> float:
+    """tolerance of the contraction path the environment currently selects"""
+    return FP64_TOL if os.environ.get("FQEB_OZAKI") == "0" else SLICED_TOL
+
+
+@pytest.fixture(params=["sliced", "fp64"])
+def contraction(request):
+    old = os.environ.get("FQEB_OZAKI")
+    if request.param == "fp64":
+        os.environ["FQEB_OZAKI"] = "0"
+    else:
+        os.environ.pop("FQEB_OZAKI", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("FQEB_OZAKI", None)
+    else:
+        os.environ["FQEB_OZAKI"] = old

@@ -27,6 +27,8 @@ Outputs (all small, committed):
     ref_nbody.npz               SURVEY 8f rank 2: individual n-body apply / exact evolution through
                                 FqeData and through Wavefunction + SparseHamiltonian (`--only nbody`)
     ref_rdm.npz                 SURVEY 8f rank 4: FqeData.rdm1 / rdm12, plain and transition (`--only rdm`)
+    ref_wfn_save.bin / .npz     a file written by the reference's Wavefunction.save and its
+                                coefficients (`--only wfnio`)
 """
 import os
 import shutil
@@ -270,6 +272,20 @@ def rdm_goldens(fqe):
     print("ref_rdm.npz", os.path.getsize(os.path.join(HERE, "ref_rdm.npz")), "bytes")
 
 
+def wfnio_goldens(fqe):
+    """A file written by the reference's Wavefunction.save (wavefunction.py:743-765) and the
+    coefficients it held: fqe_b200.wfn_io must read it without the reference installed."""
+    rng = np.random.default_rng(20260900)
+    n, sz, norb = 3, 1, 4
+    w = fqe.Wavefunction([[n, sz, norb]])
+    shape = w.get_coeff((n, sz)).shape
+    c = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    w.set_wfn(strategy="from_data", raw_data={(n, sz): c.copy()})
+    w.save("ref_wfn_save.bin", HERE)
+    np.savez(os.path.join(HERE, "ref_wfn_save.npz"), coeff=c, n=[n], sz=[sz], norb=[norb])
+    print("ref_wfn_save.bin", os.path.getsize(os.path.join(HERE, "ref_wfn_save.bin")), "bytes")
+
+
 def main():
     src = build_reference()
     install_stubs()
@@ -281,7 +297,8 @@ def main():
 
     fqe.settings.use_accelerated_code = True
     if "--only" in sys.argv:
-        {"transform": transform_goldens, "nbody": nbody_goldens, "rdm": rdm_goldens}[
+        {"transform": transform_goldens, "nbody": nbody_goldens, "rdm": rdm_goldens,
+         "wfnio": wfnio_goldens}[
             sys.argv[sys.argv.index("--only") + 1]](fqe)
         return
 
@@ -439,6 +456,7 @@ def main():
     transform_goldens(fqe)
     nbody_goldens(fqe)
     rdm_goldens(fqe)
+    wfnio_goldens(fqe)
 
 
 if __name__ == "__main__":
