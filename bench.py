@@ -296,13 +296,14 @@ def measure_fp64_gemm_peak(torch, n=8192, reps=6):
     return 2.0 * n**3 / (best * 1e-3) / 1e12
 
 
-def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
+def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e, shard=None):
     """Time K sigma builds (device-resident) and, optionally, K end-to-end builds."""
     import ctypes
     from fqe_b200 import synth
     from fqe_b200.distributed import shard_plan, sharded_apply, sharded_apply_host
     from fqe_b200.fqe_data import DenseOperator
 
+    shard = shard or args.shard
     norb = args.norb
     n, sz = norb, 0
     na, nb, la, lb = synth.sector_dims(n, sz, norb)
@@ -312,7 +313,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
     sector = wfn.sector((n, sz))
     sector.set_wfn(strategy="from_data", raw_data=host_c)
     op = DenseOperator(norb, h1, h2)
-    rows, pairs = shard_plan(args.shard, rank, world, la, op.npair)
+    rows, pairs = shard_plan(shard, rank, world, la, op.npair)
 
     def barrier():
         if world > 1:
@@ -320,7 +321,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         torch.cuda.synchronize()
 
     def step():
-        return sharded_apply(sector, op, args.shard)
+        return sharded_apply(sector, op, shard)
 
     for _ in range(args.warmup):
         sigma = step()
@@ -396,7 +397,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
             op_i = wfn._dense_operator(ham.tensors())                # operator preparation
             # H2D of this step's input (each rank its block of rows, completed by one all-gather
             # over NVLink), sharded sigma, one reduce-scatter, D2H of each rank's block
-            sharded_apply_host(sector, op_i, host_in, outs[k % 2], args.shard, bufs)
+            sharded_apply_host(sector, op_i, host_in, outs[k % 2], shard, bufs)
             torch.cuda.synchronize()
 
         e2e_step(0)
@@ -417,7 +418,7 @@ def run_leg(torch, dist, lib, fqe, args, kind, world, rank, do_e2e):
         del bufs
         # the same K builds as a stream: upload of build k+1 / download of build k-1 overlap
         # build k on separate CUDA streams (every build still copies its own input and result)
-        pipe = HostApplyStream(sector, args.shard)
+        pipe = HostApplyStream(sector, shard)
 
         def e2e_stream(k):
             ham = fqe.get_restricted_hamiltonian((h1, h2))
@@ -498,12 +499,21 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     fp64_peak = measure_fp64_gemm_peak(torch)
+    import ctypes as _ct
+    _tops = _ct.c_double(0.0)
+    i8_peak = float(_tops.value) if lib.fqeb_i8_tensor_peak(_ct.byref(_tops)) == 0 else 0.0
 
     main = run_leg(torch, dist, lib, fqe, args, args.kind, world, rank, do_e2e=True)
     other = None
     if not args.no_secondary:
         other_kind = "herm" if args.kind == "real8" else "real8"
         other = run_leg(torch, dist, lib, fqe, args, other_kind, world, rank, do_e2e=False)
+
+    pair_leg = None
+    if world > 1 and not args.no_secondary and args.shard != "pair":
+        # the partition north_star names (pair index sharded), next to the default row sharding
+        pair_leg = run_leg(torch, dist, lib, fqe, args, args.kind, world, rank, do_e2e=False,
+                           shard="pair")
 
     def summarise(res):
         npair = res["op_npair"]   # pair space of the contraction (compressed if symmetric)
@@ -547,6 +557,60 @@ def run_b200(args):
             traffic = tr["fused"]["dram_bytes_per_launch"] if fused else tr["dram_bytes_per_launch"]
     except Exception:
         pass
+    gemm_s = main["phase_ms"][1] * 1e-3
+    launches_per_step = main["phase_launches"][1] // max(args.steps, 1)
+    flop_model = "%d*P^2*L^2 with P=%d pairs (%s; %s)" % (
+        8 if main["op_kind"] == L.OP_COMPLEX else 4, main["op_npair"],
+        "complex h2'" if main["op_kind"] == L.OP_COMPLEX else
+        "real h2' times complex D: 2 real FMAs per element",
+        "i>=j compressed pair space, h2' pair-symmetric" if main["op_sym"] else
+        "full norb^2 pair space")
+    if main["path"] == 3:
+        # INT8-sliced contraction: the tensor work actually executed is 21 exact INT8 slice
+        # products of the same P x P by P x 2*ndet shape; its roofline is the INT8 tensor rate
+        # measured in this run.  The FP64 figures say what that buys on the algorithmic flops.
+        r0, r1 = main["rows"]
+        ndet_rank = (r1 - r0) * main["lb"]
+        nprod = 21
+        i8_ops = 2.0 * nprod * main["op_npair"] ** 2 * 2.0 * ndet_rank       # per sigma, this rank
+        ach_i8 = i8_ops * args.steps / gemm_s / 1e12 if gemm_s > 0 else 0.0
+        roofline = {
+            "bound": "tensor",
+            "kernel": "k_sigma_ozaki (gather of digit planes into the UMMA tile + 21 INT8 slice "
+                      "products per tile on tcgen05.mma kind::i8, INT32 accumulators in TMEM, "
+                      "FP64 reconstruction in the epilogue; the gather phase is inside this kernel)",
+            "achieved": ach_i8, "peak": i8_peak, "unit": "TOP/s",
+            "frac": ach_i8 / i8_peak if i8_peak > 0 else None, "traffic": None,
+            "peak_source": "tcgen05.mma kind::i8 M=128 N=256 K=32 on all SMs, CUDA-event timed, "
+                           "this run (fqeb_i8_tensor_peak); MEASURED_PEAKS.json has bf16 only",
+            "ops_model": "2 * 21 slice products * P^2 * 2*ndet INT8 multiply-adds with P=%d "
+                         "(6 radix-127 digit slices per operand, products i+j<=5 kept)" %
+                         main["op_npair"],
+            "ops_per_step_per_rank": i8_ops,
+            "launches_per_step": launches_per_step,
+            "fp64_equivalent": {
+                "achieved": achieved, "unit": "TFLOP/s", "flops_per_step_per_rank": flop,
+                "flop_model": flop_model, "fp64_gemm_peak": fp64_peak,
+                "ratio_to_fp64_gemm_peak": achieved / fp64_peak if fp64_peak > 0 else None,
+                "fp64_peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 6, "
+                                    "this run"},
+            "share_of_step": share,
+        }
+    else:
+        roofline = {
+            "bound": "tensor",
+            "kernel": ("k_sigma_fused (D tiles gathered into the shared-memory ring + FP64 DMMA "
+                       "contraction; the gather phase is inside this kernel)") if fused else
+                      "k_dgemm_ws (FP64 DMMA contraction)",
+            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+            "traffic_unit": "DRAM bytes per contraction launch (ncu), see profiles/r01_traffic.json",
+            "launches_per_step": launches_per_step,
+            "flops_per_step_per_rank": flop,
+            "flop_model": flop_model,
+            "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 6, this run",
+            "share_of_step": share,
+        }
     line = {
         "metric": metric_name(args.norb), "value": value, "unit": "sigma/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -585,28 +649,19 @@ def run_b200(args):
                                   "numpy arrays in and out (the call INTEGRATION.md binds at "
                                   "src/fqe/fqe_data.py:685), one GPU",
                 "cabi_host_verify_rel_err": main.get("cabi_verify")},
-        "roofline": {
-            "bound": "tensor",
-            "kernel": ("k_sigma_fused (D tiles gathered into the shared-memory ring + FP64 DMMA "
-                       "contraction; the gather phase is inside this kernel)") if fused else
-                      "k_dgemm_ws (FP64 DMMA contraction)",
-            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-            "traffic_unit": "DRAM bytes per contraction launch (ncu), see profiles/r01_traffic.json",
-            "launches_per_step": main["phase_launches"][1] // max(args.steps, 1),
-            "flops_per_step_per_rank": flop,
-            "flop_model": ("%d*P^2*L^2 with P=%d pairs (%s; %s)" % (
-                8 if main["op_kind"] == L.OP_COMPLEX else 4, main["op_npair"],
-                "complex h2'" if main["op_kind"] == L.OP_COMPLEX else
-                "real h2' times complex D: 2 real FMAs per element",
-                "i>=j compressed pair space, h2' pair-symmetric" if main["op_sym"] else
-                "full norb^2 pair space")),
-            "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 6, this run",
-            "share_of_step": share,
-        },
+        "roofline": roofline,
         "phases": phases,
         "hbm_peak": {"GBps": hbm_peak, "source": hbm_src},
     }
+    if pair_leg is not None:
+        line["pair_shard"] = {
+            "value": args.steps / (pair_leg["ms_total"] * 1e-3), "unit": "sigma/s",
+            "ms_per_step": pair_leg["ms_total"] / args.steps,
+            "verify_rel_err": pair_leg["golden_verify"],
+            "note": "dvec pair index ij sharded over the ranks (BASELINE.json north_star), C "
+                    "replicated, one all-reduce; gather and contraction shrink with the world "
+                    "size, every rank still scatters all pair rows of its partial E",
+        }
     if other is not None:
         f2, a2, ph2, sh2 = summarise(other)
         line["secondary"] = {

@@ -203,6 +203,13 @@ int fqeb_host_release(void);
  *                           (environment, default 5e-12); FQEB_OZAKI=0 disables it.            */
 enum { FQEB_PATH_NONE = 0, FQEB_PATH_THREE_KERNEL = 1, FQEB_PATH_FUSED = 2, FQEB_PATH_SLICED = 3 };
 int fqeb_sigma_last_path(void);
+/* Dense INT8 tensor-core throughput of the current device in tera-operations per second
+ * (tcgen05.mma kind::i8 on every SM, CUDA-event timed, synchronous): the roofline denominator of
+ * the sliced contraction, measured rather than assumed.                                        */
+int fqeb_i8_tensor_peak(double *tops);
+/* Diagnostic cycle counters of the sliced contraction kernel (enabled by FQEB_OZAKI_PROF=1 in the
+ * environment; see csrc/ozaki.cu): h_out[8], summed over CTAs since the previous call.          */
+int fqeb_ozaki_profile(uint64_t *h_out);
 
 /* Per-kernel device timing of the sigma build (bench.py's roofline leg).  When
  * enabled, fqeb_sigma_restricted brackets every gather / contraction / scatter

@@ -47,7 +47,7 @@ namespace fqeb {
 constexpr int OZ_NS = 6;           // digit slices of C and of the operand
 constexpr int OZ_DMAX = 5;         // slice products (i, j) with i + j <= OZ_DMAX are kept
 constexpr int OZ_RADIX = 127;
-constexpr int OZ_NMAX = 144;       // largest pair space (MMA N and K)
+constexpr int OZ_NMAX = 136;       // largest pair space (MMA N and K) whose tile + operand image fit in shared memory
 constexpr int OZ_SLOT = 144;       // TMEM columns per accumulator slot
 constexpr int OZ_WORKERS = 512;    // 16 worker warps: producers, then epilogue
 constexpr int OZ_THREADS = OZ_WORKERS + 128;   // + one warpgroup: MMA issuer (3 warps idle)
@@ -58,8 +58,10 @@ constexpr int OZ_MAX_MMAS = OZ_NPROD * 5;                     // x K steps (<= 5
 // ---------------------------------------------------------------------------------------
 // coefficient digit planes
 // ---------------------------------------------------------------------------------------
-// planes[(sign*2 + part) * ndet + det] : 8 bytes, byte s = biased digit (d_s + 64) of slice s of
+// planes[(sign * ndet + det) * 2 + part] : 8 bytes, byte s = biased digit (d_s + 64) of slice s of
 // the real (part 0) / imaginary (part 1) part of +C (sign 0) or -C (sign 1); bytes 6, 7 = 64.
+// (real and imaginary words of a determinant are adjacent: the two lanes of a determinant read
+// one 16-byte element, and 16 consecutive beta strings touch 2.3 cache lines on average.)
 // Biased digits of two sources add without carries between bytes (<= 254), and
 // (sum ^ 0x80) is the two's-complement sum of the two signed digits.
 
@@ -150,10 +152,9 @@ __global__ void k_slice_coeff(int64_t ndet, const double2 *__restrict__ coeff,
     const double2 c = coeff[i];
     const uint64_t re = balanced_digits(c.x * inv, pw), im = balanced_digits(c.y * inv, pw);
     const uint64_t k128 = 0x8080808080808080ull;
-    planes[i] = re;
-    planes[ndet + i] = im;
-    planes[2 * ndet + i] = k128 - re;   // digits of -x: no borrow between bytes (every byte <= 127)
-    planes[3 * ndet + i] = k128 - im;
+    // digits of -x: 128 - u per byte, no borrow between bytes (every byte <= 127)
+    reinterpret_cast<ulonglong2 *>(planes)[i] = make_ulonglong2(re, im);
+    reinterpret_cast<ulonglong2 *>(planes)[ndet + i] = make_ulonglong2(k128 - re, k128 - im);
   }
 }
 
@@ -308,6 +309,21 @@ __device__ __forceinline__ uint64_t oz_ldg64(const uint64_t *p) {
   asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
+// predicated 8-byte load (straight-line code: no branch per source), `dflt` when off
+__device__ __forceinline__ uint64_t oz_ldg64_if(bool pred, const uint64_t *p, uint64_t dflt) {
+  uint64_t v = dflt;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.nc.b64 %0, [%1];\n}"
+               : "+l"(v)
+               : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ int oz_ldg32_if(bool pred, const int *p) {
+  int v = 0;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.nc.s32 %0, [%1];\n}"
+               : "+r"(v)
+               : "l"(p), "r"((int)pred));
+  return v;
+}
 __device__ __forceinline__ int oz_ldg32(const int *p) {
   int v;
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -350,6 +366,7 @@ struct OzParams {
   int64_t lde;
   const double *stats;      // stats[2] = S (scale of the coefficient digits)
   double op_scale;          // T
+  unsigned long long *prof; // optional [8] cycle counters summed over CTAs (FQEB_OZAKI_PROF=1)
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p) {
@@ -428,8 +445,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const int ksteps = (kc + 1) / 2;
+      long long c_wait_tile = 0, c_wait_slot = 0, c_total = clock64();
       for (int64_t it = 0; it < my_tiles; ++it) {
+        long long c0 = clock64();
         oz_mbar_wait(bar_dfull, (uint32_t)(it & 1));
+        c_wait_tile += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         int e = 0;
 #pragma unroll 1
@@ -437,7 +457,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
           const int slot = d % 3;
           const int64_t use = 2 * it + d / 3;      // how often this slot has been filled before
           if (use >= 1) {
+            const long long c1 = clock64();
             oz_mbar_wait(bar_sfree + 8 * slot, (uint32_t)((use - 1) & 1));
+            c_wait_slot += clock64() - c1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           const uint32_t acc = tmem + (uint32_t)(slot * OZ_SLOT);
@@ -456,6 +478,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
         }
         oz_commit(bar_dfree);
       }
+      if (p.prof) {   // issuer: total, waiting for the tile, waiting for an accumulator slot
+        atomicAdd(p.prof + 0, (unsigned long long)(clock64() - c_total));
+        atomicAdd(p.prof + 1, (unsigned long long)c_wait_tile);
+        atomicAdd(p.prof + 2, (unsigned long long)c_wait_slot);
+        atomicAdd(p.prof + 7, 1ull);
+      }
     }
   } else {
     // ====================== workers: produce the tile, then drain it ===================
@@ -463,8 +491,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
     const int m = tid & 127;             // real row of the tile: (det_local, part)
     const int h = tid >> 7;              // K-column phase: columns h, h+4, h+8
     const int det_local = m >> 1, part = m & 1;
-    const uint64_t *pos = p.planes + (int64_t)part * p.ndet;
-    const uint64_t *neg = p.planes + (int64_t)(2 + part) * p.ndet;
+    const uint64_t *pos = p.planes + part;                 // element stride: 2 words
+    const uint64_t *neg = p.planes + 2 * p.ndet + part;
     const uint64_t ZERO = 0x4040404040404040ull;
     // epilogue geometry: lane quarter q (TMEM lanes 32q..32q+31) and column block cb
     const int q = warp & 3, cblk = warp >> 2;
@@ -485,39 +513,56 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       const int bt = (int)(tile - (int64_t)r * p.tiles_per_row);
       const int64_t a = p.row0 + r;
       // ---------------- produce ----------------
+      // Octets of 8 pair indices: the 16 digit-word loads of octet o are in flight while the map
+      // entries of octet o+1 are fetched, so a thread pays about one memory round trip per octet
+      // (16 warps x 16 loads per SM in flight) instead of two dependent ones per quad.
+      long long c_p0 = clock64();
       if (it >= 1) oz_mbar_wait(bar_dfree, (uint32_t)((it - 1) & 1));
+      const long long c_p1 = clock64();
       {
         const int64_t b = (int64_t)bt * OZ_TILE_DETS + det_local;
         const bool valid = b < p.lenb;
         const int32_t *ta_row = p.mapT_a + a * (int64_t)p.ntab;
         const int32_t *mb = p.map_b + (valid ? b : 0);
-        const int64_t arow = a * p.lenb;
-        for (int g = h; g < kc; g += 4) {
-          uint32_t out[OZ_NS][4];
+        const uint64_t *crow_pos = pos + 2 * a * p.lenb, *crow_neg = neg + 2 * a * p.lenb;
+        const uint64_t *ccol_pos = pos + 2 * (valid ? b : 0), *ccol_neg = neg + 2 * (valid ? b : 0);
+        const int ngroups = h < kc ? (kc - h + 3) / 4 : 0;     // groups h, h+4, h+8 < kc
+        auto load_maps = [&](int o, int (&ta_)[8], int (&tb_)[8]) {
+          const int k0 = 16 * (h + 4 * (o >> 1)) + 8 * (o & 1);
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u;
+            const bool on = valid && k < p.np;
+            ta_[u] = oz_ldg32_if(on, ta_row + k);
+            tb_[u] = oz_ldg32_if(on, mb + (int64_t)k * p.lenb);
+          }
+        };
+        int ta[8], tb[8];
+        if (ngroups > 0) load_maps(0, ta, tb);
+        uint32_t out[OZ_NS][4];
+        for (int o = 0; o < 2 * ngroups; ++o) {
+          uint64_t va[8], vb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            va[u] = oz_ldg64_if(ta[u] != 0, (ta[u] > 0 ? ccol_pos : ccol_neg) +
+                                                2 * (int64_t)(abs(ta[u]) - 1) * p.lenb, ZERO);
+            vb[u] = oz_ldg64_if(tb[u] != 0,
+                                (tb[u] > 0 ? crow_pos : crow_neg) + 2 * (abs(tb[u]) - 1), ZERO);
+          }
+          int nta[8], ntb[8];
+          if (o + 1 < 2 * ngroups) {
+            load_maps(o + 1, nta, ntb);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nta[u] = ntb[u] = 0;
+          }
+          const int half = o & 1;
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd) {
             uint64_t e[4];
-            int ta[4], tb[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int k = 16 * g + 4 * qd + u;
-              const bool on = valid && k < p.np;
-              ta[u] = on ? oz_ldg32(ta_row + k) : 0;
-              tb[u] = on ? oz_ldg32(mb + (int64_t)k * p.lenb) : 0;
-            }
-            uint64_t va[4], vb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              va[u] = ZERO;
-              vb[u] = ZERO;
-              if (ta[u] != 0)
-                va[u] = oz_ldg64((ta[u] > 0 ? pos : neg) + ((int64_t)(abs(ta[u]) - 1) * p.lenb + b));
-              if (tb[u] != 0)
-                vb[u] = oz_ldg64((tb[u] > 0 ? pos : neg) + (arow + (abs(tb[u]) - 1)));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              e[u] = (va[u] + vb[u]) ^ 0x8080808080808080ull;   // signed digit sums, per byte
+            for (int u = 0; u < 4; ++u)   // signed digit sums, per byte
+              e[u] = (va[4 * qd + u] + vb[4 * qd + u]) ^ 0x8080808080808080ull;
             // 4 x 4 byte transposes: word s of `out` = slice s of the four k of this quad
             const uint32_t l0 = (uint32_t)e[0], l1 = (uint32_t)e[1], l2 = (uint32_t)e[2],
                            l3 = (uint32_t)e[3];
@@ -525,25 +570,64 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
                            h2 = (uint32_t)(e[2] >> 32), h3 = (uint32_t)(e[3] >> 32);
             const uint32_t t0 = __byte_perm(l0, l1, 0x5140), t1 = __byte_perm(l2, l3, 0x5140);
             const uint32_t t2 = __byte_perm(l0, l1, 0x7362), t3 = __byte_perm(l2, l3, 0x7362);
-            out[0][qd] = __byte_perm(t0, t1, 0x5410);
-            out[1][qd] = __byte_perm(t0, t1, 0x7632);
-            out[2][qd] = __byte_perm(t2, t3, 0x5410);
-            out[3][qd] = __byte_perm(t2, t3, 0x7632);
             const uint32_t t4 = __byte_perm(h0, h1, 0x5140), t5 = __byte_perm(h2, h3, 0x5140);
-            out[4][qd] = __byte_perm(t4, t5, 0x5410);
-            out[5][qd] = __byte_perm(t4, t5, 0x7632);
+            const uint32_t w0 = __byte_perm(t0, t1, 0x5410), w1 = __byte_perm(t0, t1, 0x7632);
+            const uint32_t w2 = __byte_perm(t2, t3, 0x5410), w3 = __byte_perm(t2, t3, 0x7632);
+            const uint32_t w4 = __byte_perm(t4, t5, 0x5410), w5 = __byte_perm(t4, t5, 0x7632);
+            if (half == 0) {
+              out[0][qd] = w0; out[1][qd] = w1; out[2][qd] = w2;
+              out[3][qd] = w3; out[4][qd] = w4; out[5][qd] = w5;
+            } else {
+              out[0][2 + qd] = w0; out[1][2 + qd] = w1; out[2][2 + qd] = w2;
+              out[3][2 + qd] = w3; out[4][2 + qd] = w4; out[5][2 + qd] = w5;
+            }
           }
-          // 16-byte core-matrix rows: conflict-free (32 consecutive rows = 512 contiguous bytes)
-          const uint32_t dst = oz_smem_u32(s_d) + (uint32_t)(g * 16 + (m >> 3)) * 128 + (m & 7) * 16;
+          if (half == 1) {
+            // 16-byte core-matrix rows: conflict-free (32 consecutive rows = 512 contiguous bytes)
+            const int g = h + 4 * (o >> 1);
+            const uint32_t dst =
+                oz_smem_u32(s_d) + (uint32_t)(g * 16 + (m >> 3)) * 128 + (m & 7) * 16;
 #pragma unroll
-          for (int s = 0; s < OZ_NS; ++s)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)(s * kc) * 2048),
-                         "r"(out[s][0]), "r"(out[s][1]), "r"(out[s][2]), "r"(out[s][3])
-                         : "memory");
+            for (int sl = 0; sl < OZ_NS; ++sl)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(
+                               dst + (uint32_t)(sl * kc) * 2048),
+                           "r"(out[sl][0]), "r"(out[sl][1]), "r"(out[sl][2]), "r"(out[sl][3])
+                           : "memory");
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            ta[u] = nta[u];
+            tb[u] = ntb[u];
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       oz_mbar_arrive(bar_dfull);
+      // While the tensor core works on this tile, pull the alpha-source lines of the NEXT tile
+      // into L2 (they are the only gather traffic that misses L2: 72 rows x 1 KB per tile), so
+      // that the next production phase does not queue behind this tile's E stores in HBM.
+      if (it + 1 < my_tiles && part == 0 && (det_local & 7) == 0) {
+        const int64_t tile2 = tile + gridDim.x;
+        const int r2 = (int)(tile2 / p.tiles_per_row);
+        const int bt2 = (int)(tile2 - (int64_t)r2 * p.tiles_per_row);
+        const int64_t b2 = (int64_t)bt2 * OZ_TILE_DETS + det_local;
+        if (b2 < p.lenb) {
+          const int32_t *ta_row2 = p.mapT_a + (p.row0 + r2) * (int64_t)p.ntab;
+          for (int g = h; g < kc; g += 4) {
+#pragma unroll 4
+            for (int u = 0; u < 16; ++u) {
+              const int k = 16 * g + u;
+              const int t2 = k < p.np ? oz_ldg32(ta_row2 + k) : 0;
+              if (t2 != 0) {
+                const uint64_t *src =
+                    (t2 > 0 ? p.planes : p.planes + 2 * p.ndet) + 2 * ((int64_t)(abs(t2) - 1) * p.lenb + b2);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+              }
+            }
+          }
+        }
+      }
+      const long long c_p2 = clock64();
       // ---------------- drain ----------------
       double run[36];
 #pragma unroll
@@ -573,8 +657,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int c = 0; c < (rd < 4 ? 8 : 4); ++c) {
+            // int32 -> double on the FP64 pipe (exact): 2^52 + 2^31 + comb, minus the offset
+            // (I2F.F64 runs on the quarter-rate conversion unit)
             const int comb = (int)ra[c] * OZ_RADIX + (int)rb[c];
-            run[8 * rd + c] = fma(w[pr], (double)comb, run[8 * rd + c]);
+            const double cd = __hiloint2double(0x43300000, comb ^ (int)0x80000000) -
+                              4503601774854144.0;
+            run[8 * rd + c] = fma(w[pr], cd, run[8 * rd + c]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -584,6 +672,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
           oz_mbar_arrive(bar_sfree + 8 * sb);
         }
       }
+      const long long c_p3 = clock64();
       // E[kl][r*pitch + b].{re,im}: row erow = (det, part); consecutive lanes -> consecutive doubles
       {
         const int edet = erow >> 1, epart = erow & 1;
@@ -596,6 +685,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
             if (c < cpb && kl < p.np) __stcs(base + 2 * (int64_t)kl * p.lde, run[c]);
           }
         }
+      }
+      if (p.prof && tid == 0) {   // worker 0: wait for the tile buffer, produce, drain, store
+        atomicAdd(p.prof + 3, (unsigned long long)(c_p1 - c_p0));
+        atomicAdd(p.prof + 4, (unsigned long long)(c_p2 - c_p1));
+        atomicAdd(p.prof + 5, (unsigned long long)(c_p3 - c_p2));
+        atomicAdd(p.prof + 6, (unsigned long long)(clock64() - c_p3));
       }
     }
   }
@@ -660,6 +755,8 @@ double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq) {
   return q * sqrt(2.0 * ndet) / sqrt(sumsq);
 }
 
+static unsigned long long *g_oz_prof = nullptr;
+
 int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
                  const double *d_stats, int64_t row0, int64_t nrows, int pitch, double *d_evec,
                  int64_t lde, cudaStream_t st) {
@@ -690,9 +787,22 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   p.lde = lde;
   p.stats = d_stats;
   p.op_scale = o.scale;
+  p.prof = nullptr;
+  {
+    static const bool prof_on = getenv("FQEB_OZAKI_PROF") && getenv("FQEB_OZAKI_PROF")[0] == '1';
+    if (prof_on) {
+      if (!g_oz_prof) {
+        FQEB_CUDA(cudaMalloc(&g_oz_prof, 8 * sizeof(unsigned long long)));
+        FQEB_CUDA(cudaMemset(g_oz_prof, 0, 8 * sizeof(unsigned long long)));
+      }
+      p.prof = g_oz_prof;
+    }
+  }
   // D^T tile + operand image (its zero block is also what the row groups past the pair space
   // and the last slice's odd K column read)
-  const size_t smem = (size_t)OZ_NS * o.kc * 2048 + o.img_bytes;
+  // (the odd K column of the last slice reads one 2048-byte column past the tile, i.e. the start
+  // of the image: keep at least that much behind the tile for tiny pair spaces)
+  const size_t smem = (size_t)OZ_NS * o.kc * 2048 + (o.img_bytes > 2048 ? o.img_bytes : 2048);
   FQEB_REQUIRE(smem + 1856 <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
   static size_t attr_bytes = 0;   // dynamic + static shared memory must stay within 227 KB
   if (smem > attr_bytes) {
@@ -708,4 +818,121 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   return FQEB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// INT8 tensor-core rate of this GPU, measured: the roofline denominator of k_sigma_ozaki.
+// Every SM issues chains of tcgen05.mma kind::i8 (M = 128, N = 256, K = 32) on resident
+// operands; the tensor time of such an MMA is 128 cycles, so the single issuing thread is
+// not the limit.  (MEASURED_PEAKS.json carries bf16 only; INT8 is nominally twice that.)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_i8_rate(int iters, int32_t *__restrict__ sink) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_s;
+  constexpr int N = 256, KB = 160;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + N) * KB; i += blockDim.x) smem[i] = (uint8_t)((i * 37 + 11) & 0x3f);
+  if (tid == 0) {
+    oz_mbar_init(oz_smem_u32(&bar[0]), 1);
+    oz_mbar_init(oz_smem_u32(&bar[1]), 1);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        oz_smem_u32(&tmem_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_s;
+  if (tid == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    uint64_t ad[5], bd[5];
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      ad[ks] = oz_desc(oz_smem_u32(smem) + ks * 2 * 16 * 128, 16 * 128, 128);
+      bd[ks] = oz_desc(oz_smem_u32(smem) + 128 * KB + ks * 2 * (N / 8) * 128, (N / 8) * 128, 128);
+    }
+    for (int it = 0; it < iters; ++it) {     // two accumulators, two chains in flight
+      const int slot = it & 1;
+      if (it >= 2) oz_mbar_wait(oz_smem_u32(&bar[slot]), (uint32_t)((it / 2 - 1) & 1));
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) oz_mma(tmem + slot * N, ad[ks], bd[ks], idesc, (c | ks) != 0);
+      }
+      oz_commit(oz_smem_u32(&bar[slot]));
+    }
+    for (int it = (iters > 2 ? iters - 2 : 0); it < iters; ++it)
+      oz_mbar_wait(oz_smem_u32(&bar[it & 1]), (uint32_t)((it / 2) & 1));
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    uint32_t r0[4];
+    OZ_TMEM_LD4(r0, tmem + ((uint32_t)(warp * 32) << 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (r0[0] == 0x12345678u) sink[tid] = (int32_t)r0[1];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 }  // namespace fqeb
+
+// Cycle counters of k_sigma_ozaki since the last call (FQEB_OZAKI_PROF=1), summed over CTAs:
+// [0] issuer total, [1] issuer waiting for a tile, [2] issuer waiting for an accumulator slot,
+// [3] worker 0 waiting for the tile buffer, [4] producing, [5] draining, [6] storing E,
+// [7] number of CTA launches.  Synchronises the device.
+extern "C" int fqeb_ozaki_profile(uint64_t *h_out) {
+  using namespace fqeb;
+  FQEB_REQUIRE(h_out != nullptr, "fqeb_ozaki_profile: NULL argument");
+  for (int i = 0; i < 8; ++i) h_out[i] = 0;
+  if (!g_oz_prof) return FQEB_OK;
+  FQEB_CUDA(cudaDeviceSynchronize());
+  FQEB_CUDA(cudaMemcpy(h_out, g_oz_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  FQEB_CUDA(cudaMemset(g_oz_prof, 0, 8 * sizeof(uint64_t)));
+  return FQEB_OK;
+}
+
+// dense INT8 tensor-core throughput (tera-operations per second, 2 ops per multiply-add) of the
+// current device, measured with tcgen05.mma kind::i8 on all SMs; CUDA-event timed, synchronous
+extern "C" int fqeb_i8_tensor_peak(double *tops) {
+  using namespace fqeb;
+  int rc = require_device();
+  if (rc != FQEB_OK) return rc;
+  FQEB_REQUIRE(tops != nullptr, "fqeb_i8_tensor_peak: NULL argument");
+  const int iters = 600, mmas_per_iter = 20;
+  const size_t smem = (size_t)(128 + 256) * 160;
+  FQEB_CUDA(cudaFuncSetAttribute(k_i8_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int32_t *d_sink = nullptr;
+  FQEB_CUDA(cudaMalloc(&d_sink, sizeof(int32_t) * 128));
+  cudaEvent_t e0, e1;
+  FQEB_CUDA(cudaEventCreate(&e0));
+  FQEB_CUDA(cudaEventCreate(&e1));
+  const int sms = sm_count();
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, nullptr);
+    k_i8_rate<<<sms, 128, smem>>>(iters, d_sink);
+    cudaEventRecord(e1, nullptr);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_sink);
+  if (err != cudaSuccess || best_ms > 1e29) {
+    set_error("fqeb_i8_tensor_peak: %s", cudaGetErrorString(err));
+    return FQEB_ERR_CUDA;
+  }
+  const double ops = 2.0 * 128 * 256 * 32 * (double)mmas_per_iter * iters * sms;
+  *tops = ops / (best_ms * 1e-3) / 1e12;
+  count_launch(4);
+  return FQEB_OK;
+}

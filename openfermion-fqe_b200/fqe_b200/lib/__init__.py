@@ -36,6 +36,8 @@ SIGNATURES = {
     "fqeb_launch_count": (c_uint64, []),
     "fqeb_sigma_last_path": (c_int, []),
     "fqeb_host_release": (c_int, []),
+    "fqeb_i8_tensor_peak": (c_int, [POINTER(c_double)]),
+    "fqeb_ozaki_profile": (c_int, [POINTER(c_uint64)]),
     "fqeb_set_device": (c_int, [c_int]),
     "fqeb_graph_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
     "fqeb_graph_destroy": (c_int, [c_void_p]),
