@@ -140,21 +140,57 @@ __device__ __forceinline__ uint64_t balanced_digits(double x, double scale_pow) 
   return w;
 }
 
-__global__ void k_slice_coeff(int64_t ndet, const double2 *__restrict__ coeff,
-                              const double *__restrict__ stats, uint64_t *__restrict__ planes) {
+// One block slices a 32 x 32 block of determinants and writes it twice: in the coefficient layout
+// (planes, [a][b]) and transposed (planesT, [b][a]), both with coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) k_slice_coeff(int64_t lena, int64_t lenb,
+                                                      const double2 *__restrict__ coeff,
+                                                      const double *__restrict__ stats,
+                                                      ulonglong2 *__restrict__ planes,
+                                                      ulonglong2 *__restrict__ planesT) {
+  __shared__ ulonglong2 tile[32][33];
   const double s = stats[2];
   const double inv = s > 0.0 ? 1.0 / s : 0.0;
   double pw = 1.0;
 #pragma unroll
   for (int i = 0; i < OZ_NS; ++i) pw *= (double)OZ_RADIX;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ndet;
+  const int64_t ndet = lena * lenb;
+  const int64_t nbt = (lenb + 31) / 32;
+  const int64_t a0 = (blockIdx.x / nbt) * 32, b0 = (blockIdx.x % nbt) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint64_t k128 = 0x8080808080808080ull;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t a = a0 + ty + 8 * r, b = b0 + tx;
+    if (a < lena && b < lenb) {
+      const double2 c = coeff[a * lenb + b];
+      const uint64_t re = balanced_digits(c.x * inv, pw), im = balanced_digits(c.y * inv, pw);
+      // digits of -x: 128 - u per byte, no borrow between bytes (every byte <= 127)
+      planes[a * lenb + b] = make_ulonglong2(re, im);
+      planes[ndet + a * lenb + b] = make_ulonglong2(k128 - re, k128 - im);
+      tile[ty + 8 * r][tx] = make_ulonglong2(re, im);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t a = a0 + tx, b = b0 + ty + 8 * r;
+    if (a < lena && b < lenb) {
+      const ulonglong2 v = tile[tx][ty + 8 * r];
+      planesT[b * lena + a] = v;
+      planesT[ndet + b * lena + a] = make_ulonglong2(k128 - v.x, k128 - v.y);
+    }
+  }
+}
+
+// zero-padded copy of a by-string map: dst[x][0..kpad) = src[x][0..np), 0 beyond
+__global__ void k_pad_map(int64_t len, int np, int kpad, const int32_t *__restrict__ src,
+                          int32_t *__restrict__ dst) {
+  const int64_t n = len * kpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const double2 c = coeff[i];
-    const uint64_t re = balanced_digits(c.x * inv, pw), im = balanced_digits(c.y * inv, pw);
-    const uint64_t k128 = 0x8080808080808080ull;
-    // digits of -x: 128 - u per byte, no borrow between bytes (every byte <= 127)
-    reinterpret_cast<ulonglong2 *>(planes)[i] = make_ulonglong2(re, im);
-    reinterpret_cast<ulonglong2 *>(planes)[ndet + i] = make_ulonglong2(k128 - re, k128 - im);
+    const int64_t x = i / kpad;
+    const int k = (int)(i - x * kpad);
+    dst[i] = k < np ? src[x * np + k] : 0;
   }
 }
 
@@ -317,6 +353,15 @@ __device__ __forceinline__ uint64_t oz_ldg64_if(bool pred, const uint64_t *p, ui
                : "l"(p), "r"((int)pred));
   return v;
 }
+// predicated 16-byte load of four map entries, zeros when off
+__device__ __forceinline__ void oz_ldg128_if(bool pred, const int *p, int &x, int &y, int &z,
+                                             int &w) {
+  x = y = z = w = 0;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
+      : "+r"(x), "+r"(y), "+r"(z), "+r"(w)
+      : "l"(p), "r"((int)pred));
+}
 __device__ __forceinline__ int oz_ldg32_if(bool pred, const int *p) {
   int v = 0;
   asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.nc.s32 %0, [%1];\n}"
@@ -354,12 +399,13 @@ struct OzParams {
   const int8_t *img;        // operand digit image (global)
   int img_bytes;
   int np, kc, ng, n_mma;    // pair space, 16-byte K columns, 8-row groups, MMA N
-  const uint64_t *planes;   // coefficient digit planes [4][ndet]
+  const uint64_t *planes;   // coefficient digit planes [sign][a][b][part]
+  const uint64_t *planesT;  // the same, transposed:     [sign][b][a][part]
   int64_t ndet;
-  const int32_t *mapT_a;    // [lena][ntab]  alpha adjoint map, by string
-  const int32_t *map_b;     // [ntab][lenb]  beta adjoint map, by pair
-  int ntab;
-  int64_t lenb, row0;
+  const int32_t *mapT_a;    // [lena][kpad]  alpha adjoint map by string, zero-padded to kpad = 16 kc
+  const int32_t *mapT_b;    // [lenb][kpad]  beta adjoint map by string
+  int kpad;
+  int64_t lena, lenb, row0, nrows;
   int pitch, tiles_per_row;
   int64_t ntiles;
   double2 *E;
@@ -488,17 +534,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
   } else {
     // ====================== workers: produce the tile, then drain it ===================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
-    const int m = tid & 127;             // real row of the tile: (det_local, part)
+    // Row m of the tile = (determinant, part) of an 8 x 8 block of determinants (8 alpha rows x
+    // 8 beta columns); the 32 rows of a lane quarter are a 4 x 4 sub-block, so that one warp-wide
+    // gather of alpha sources (rows of `planes`, contiguous in b) and one of beta sources (rows of
+    // `planesT`, contiguous in a) each touch four 64-byte segments instead of 16 scattered lines
+    const int m = tid & 127;
     const int h = tid >> 7;              // K-column phase: columns h, h+4, h+8
-    const int det_local = m >> 1, part = m & 1;
-    const uint64_t *pos = p.planes + part;                 // element stride: 2 words
-    const uint64_t *neg = p.planes + 2 * p.ndet + part;
+    const int part = m & 1;
+    const int ar = 4 * (m >> 6) + ((m >> 3) & 3), bc = 4 * ((m >> 5) & 1) + ((m >> 1) & 3);
+    const uint64_t *pl = p.planes + part, *plT = p.planesT + part;   // element stride: 2 words
+    const int64_t neg_off = 2 * p.ndet;
     const uint64_t ZERO = 0x4040404040404040ull;
     // epilogue geometry: lane quarter q (TMEM lanes 32q..32q+31) and column block cb
     const int q = warp & 3, cblk = warp >> 2;
     const int cpb = (p.np + 3) / 4;                 // columns per block (<= 36)
     const int col0 = cblk * cpb;
     const int erow = q * 32 + lane;                 // accumulator row handled in the epilogue
+    const int e_ar = 4 * (erow >> 6) + ((erow >> 3) & 3), e_bc = 4 * ((erow >> 5) & 1) + ((erow >> 1) & 3);
     const double st = p.stats[2] * p.op_scale;      // S * T
     double w[3];
     {
@@ -511,31 +563,26 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int r = (int)(tile / p.tiles_per_row);
       const int bt = (int)(tile - (int64_t)r * p.tiles_per_row);
-      const int64_t a = p.row0 + r;
       // ---------------- produce ----------------
       // Octets of 8 pair indices: the 16 digit-word loads of octet o are in flight while the map
-      // entries of octet o+1 are fetched, so a thread pays about one memory round trip per octet
-      // (16 warps x 16 loads per SM in flight) instead of two dependent ones per quad.
+      // entries of octet o+1 are fetched (two 16-byte loads per map), so a thread pays about one
+      // memory round trip per octet.
       long long c_p0 = clock64();
       if (it >= 1) oz_mbar_wait(bar_dfree, (uint32_t)((it - 1) & 1));
       const long long c_p1 = clock64();
       {
-        const int64_t b = (int64_t)bt * OZ_TILE_DETS + det_local;
-        const bool valid = b < p.lenb;
-        const int32_t *ta_row = p.mapT_a + a * (int64_t)p.ntab;
-        const int32_t *mb = p.map_b + (valid ? b : 0);
-        const uint64_t *crow_pos = pos + 2 * a * p.lenb, *crow_neg = neg + 2 * a * p.lenb;
-        const uint64_t *ccol_pos = pos + 2 * (valid ? b : 0), *ccol_neg = neg + 2 * (valid ? b : 0);
+        const int64_t a_loc = 8 * (int64_t)r + ar, b = 8 * (int64_t)bt + bc;
+        const bool valid = a_loc < p.nrows && b < p.lenb;
+        const int64_t a = p.row0 + (valid ? a_loc : 0), bb = valid ? b : 0;
+        const int32_t *ta_row = p.mapT_a + a * p.kpad, *tb_row = p.mapT_b + bb * p.kpad;
+        const uint64_t *src_a = pl + 2 * bb, *src_b = plT + 2 * a;
         const int ngroups = h < kc ? (kc - h + 3) / 4 : 0;     // groups h, h+4, h+8 < kc
         auto load_maps = [&](int o, int (&ta_)[8], int (&tb_)[8]) {
           const int k0 = 16 * (h + 4 * (o >> 1)) + 8 * (o & 1);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u;
-            const bool on = valid && k < p.np;
-            ta_[u] = oz_ldg32_if(on, ta_row + k);
-            tb_[u] = oz_ldg32_if(on, mb + (int64_t)k * p.lenb);
-          }
+          oz_ldg128_if(valid, ta_row + k0, ta_[0], ta_[1], ta_[2], ta_[3]);
+          oz_ldg128_if(valid, ta_row + k0 + 4, ta_[4], ta_[5], ta_[6], ta_[7]);
+          oz_ldg128_if(valid, tb_row + k0, tb_[0], tb_[1], tb_[2], tb_[3]);
+          oz_ldg128_if(valid, tb_row + k0 + 4, tb_[4], tb_[5], tb_[6], tb_[7]);
         };
         int ta[8], tb[8];
         if (ngroups > 0) load_maps(0, ta, tb);
@@ -544,10 +591,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
           uint64_t va[8], vb[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            va[u] = oz_ldg64_if(ta[u] != 0, (ta[u] > 0 ? ccol_pos : ccol_neg) +
+            va[u] = oz_ldg64_if(ta[u] != 0, src_a + (ta[u] < 0 ? neg_off : 0) +
                                                 2 * (int64_t)(abs(ta[u]) - 1) * p.lenb, ZERO);
-            vb[u] = oz_ldg64_if(tb[u] != 0,
-                                (tb[u] > 0 ? crow_pos : crow_neg) + 2 * (abs(tb[u]) - 1), ZERO);
+            vb[u] = oz_ldg64_if(tb[u] != 0, src_b + (tb[u] < 0 ? neg_off : 0) +
+                                                2 * (int64_t)(abs(tb[u]) - 1) * p.lena, ZERO);
           }
           int nta[8], ntb[8];
           if (o + 1 < 2 * ngroups) {
@@ -603,30 +650,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       oz_mbar_arrive(bar_dfull);
-      // While the tensor core works on this tile, pull the alpha-source lines of the NEXT tile
-      // into L2 (they are the only gather traffic that misses L2: 72 rows x 1 KB per tile), so
-      // that the next production phase does not queue behind this tile's E stores in HBM.
-      if (it + 1 < my_tiles && part == 0 && (det_local & 7) == 0) {
-        const int64_t tile2 = tile + gridDim.x;
-        const int r2 = (int)(tile2 / p.tiles_per_row);
-        const int bt2 = (int)(tile2 - (int64_t)r2 * p.tiles_per_row);
-        const int64_t b2 = (int64_t)bt2 * OZ_TILE_DETS + det_local;
-        if (b2 < p.lenb) {
-          const int32_t *ta_row2 = p.mapT_a + (p.row0 + r2) * (int64_t)p.ntab;
-          for (int g = h; g < kc; g += 4) {
-#pragma unroll 4
-            for (int u = 0; u < 16; ++u) {
-              const int k = 16 * g + u;
-              const int t2 = k < p.np ? oz_ldg32(ta_row2 + k) : 0;
-              if (t2 != 0) {
-                const uint64_t *src =
-                    (t2 > 0 ? p.planes : p.planes + 2 * p.ndet) + 2 * ((int64_t)(abs(t2) - 1) * p.lenb + b2);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-              }
-            }
-          }
-        }
-      }
       const long long c_p2 = clock64();
       // ---------------- drain ----------------
       double run[36];
@@ -675,10 +698,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       const long long c_p3 = clock64();
       // E[kl][r*pitch + b].{re,im}: row erow = (det, part); consecutive lanes -> consecutive doubles
       {
-        const int edet = erow >> 1, epart = erow & 1;
-        const int64_t b = (int64_t)bt * OZ_TILE_DETS + edet;
-        if (b < p.lenb) {
-          double *base = reinterpret_cast<double *>(p.E + ((int64_t)r * p.pitch + b)) + epart;
+        const int epart = erow & 1;
+        const int64_t a_loc = 8 * (int64_t)r + e_ar, b = 8 * (int64_t)bt + e_bc;
+        if (a_loc < p.nrows && b < p.lenb) {
+          double *base = reinterpret_cast<double *>(p.E + (a_loc * p.pitch + b)) + epart;
 #pragma unroll
           for (int c = 0; c < 36; ++c) {
             const int kl = col0 + c;
@@ -705,14 +728,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
 // ---------------------------------------------------------------------------------------
 constexpr int OZ_STATS_DOUBLES = 4 + 2 * 1024;
 // workspace bytes of the sliced path: digit planes + statistics block
+static size_t oz_planes_bytes(const fqeb_graph *g) {
+  // [layout: by row, transposed][sign][det][part] digit words
+  return (size_t)round_up(sizeof(uint64_t) * 8 * (size_t)g->len[0] * g->len[1] + 64, 256);
+}
 size_t ozaki_workspace_bytes(const fqeb_graph *g) {
-  return (size_t)round_up(sizeof(uint64_t) * 4 * (size_t)g->len[0] * g->len[1] + 64, 256) +
+  return oz_planes_bytes(g) +
          (size_t)round_up(sizeof(double) * OZ_STATS_DOUBLES, 256);
 }
 // the statistics block sits behind the planes
 double *ozaki_stats_ptr(const fqeb_graph *g, void *d_oz) {
-  return (double *)((char *)d_oz +
-                    round_up(sizeof(uint64_t) * 4 * (size_t)g->len[0] * g->len[1] + 64, 256));
+  return (double *)((char *)d_oz + oz_planes_bytes(g));
 }
 
 // d_stats: device buffer of OZ_STATS_DOUBLES doubles.  Returns max |Re/Im C| and ||C||^2 on the
@@ -736,12 +762,13 @@ int ozaki_stats(const fqeb_graph *g, const double *d_coeff, double *d_stats, dou
 // digit planes of the coefficients (scale = d_stats[2], written by ozaki_stats)
 int ozaki_slice(const fqeb_graph *g, const double *d_coeff, const double *d_stats, void *d_planes,
                 cudaStream_t st) {
-  const int64_t ndet = g->len[0] * g->len[1];
-  int64_t blocks = (ndet + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  k_slice_coeff<<<(unsigned)blocks, 256, 0, st>>>(ndet, (const double2 *)d_coeff, d_stats,
-                                                   (uint64_t *)d_planes);
+  const int64_t lena = g->len[0], lenb = g->len[1], ndet = lena * lenb;
+  const int64_t blocks = ((lena + 31) / 32) * ((lenb + 31) / 32);
+  if (blocks < 1) return FQEB_OK;
+  FQEB_REQUIRE(blocks < (1ll << 31), "ozaki: sector too large for the slicing grid");
+  ulonglong2 *planes = (ulonglong2 *)d_planes;
+  k_slice_coeff<<<(unsigned)blocks, 256, 0, st>>>(lena, lenb, (const double2 *)d_coeff, d_stats,
+                                                   planes, planes + 2 * ndet);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }
@@ -757,12 +784,34 @@ double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq) {
 
 static unsigned long long *g_oz_prof = nullptr;
 
+// by-string adjoint maps zero-padded to kpad columns (built once per graph and pair-space kind)
+static int ozaki_maps(const fqeb_graph *g, bool sym, int np, int kpad, const int32_t **ma,
+                      const int32_t **mb) {
+  GraphLock lock(g);
+  fqeb_graph *gm = const_cast<fqeb_graph *>(g);
+  const int nspin = g->shared_spin ? 1 : 2;
+  for (int sp = 0; sp < nspin; ++sp) {
+    if (gm->d_ozmapT[sym][sp]) continue;
+    const int64_t len = g->len[sp];
+    int32_t *dst = nullptr;
+    FQEB_CUDA(cudaMalloc(&dst, sizeof(int32_t) * (size_t)len * kpad));
+    int64_t blocks = (len * kpad + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pad_map<<<(unsigned)blocks, 256>>>(len, np, kpad, sym ? g->d_smapT[sp] : g->d_amapT[sp], dst);
+    FQEB_CHECK_LAUNCH();
+    FQEB_CUDA(cudaDeviceSynchronize());
+    gm->d_ozmapT[sym][sp] = dst;
+  }
+  *ma = gm->d_ozmapT[sym][0];
+  *mb = gm->d_ozmapT[sym][g->shared_spin ? 0 : 1];
+  return FQEB_OK;
+}
+
 int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
                  const double *d_stats, int64_t row0, int64_t nrows, int pitch, double *d_evec,
                  int64_t lde, cudaStream_t st) {
   FQEB_REQUIRE(ozaki_shape_ok(op), "ozaki: operator not supported by the sliced contraction");
-  FQEB_REQUIRE(pitch % OZ_TILE_DETS == 0 && pitch >= g->len[1] && lde >= nrows * (int64_t)pitch,
-               "ozaki: bad column layout");
+  FQEB_REQUIRE(pitch >= g->len[1] && lde >= nrows * (int64_t)pitch, "ozaki: bad column layout");
   OzOperand o;
   int rc = ozaki_operand(op, g->nele[0] + g->nele[1], &o);
   if (rc != FQEB_OK) return rc;
@@ -773,16 +822,19 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   p.kc = o.kc;
   p.ng = o.ng;
   p.n_mma = o.n_mma;
-  p.planes = (const uint64_t *)d_planes;
   p.ndet = g->len[0] * g->len[1];
-  p.mapT_a = op->sym ? g->d_smapT[0] : g->d_amapT[0];
-  p.map_b = op->sym ? g->d_smap[1] : g->d_amap[1];
-  p.ntab = op->np;
+  p.planes = (const uint64_t *)d_planes;
+  p.planesT = p.planes + 4 * p.ndet;
+  p.kpad = 16 * o.kc;
+  rc = ozaki_maps(g, op->sym, op->np, p.kpad, &p.mapT_a, &p.mapT_b);
+  if (rc != FQEB_OK) return rc;
+  p.lena = g->len[0];
   p.lenb = g->len[1];
   p.row0 = row0;
+  p.nrows = nrows;
   p.pitch = pitch;
-  p.tiles_per_row = pitch / OZ_TILE_DETS;
-  p.ntiles = nrows * p.tiles_per_row;
+  p.tiles_per_row = (int)((g->len[1] + 7) / 8);
+  p.ntiles = ((nrows + 7) / 8) * p.tiles_per_row;
   p.E = (double2 *)d_evec;
   p.lde = lde;
   p.stats = d_stats;

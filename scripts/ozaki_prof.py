@@ -31,7 +31,7 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 lib.fqeb_profile_collect(ms3, cnt3)
 lib.fqeb_ozaki_profile(prof)
-ntiles = d.lena() * ((d.lenb() + 63) // 64) * reps
+ntiles = ((d.lena() + 7) // 8) * ((d.lenb() + 7) // 8) * reps   # 8 x 8 determinant tiles (chunk edges ignored)
 print(f"norb={norb} path={lib.fqeb_sigma_last_path()} sigma {dt*1e3:.1f} ms; phases per sigma (ms): "
       f"prepass {ms3[0]/reps:.2f} contract {ms3[1]/reps:.2f} scatter {ms3[2]/reps:.2f}; launches {list(cnt3)}")
 names = ["issuer total", "issuer wait tile", "issuer wait slot", "worker wait buffer", "worker produce",
