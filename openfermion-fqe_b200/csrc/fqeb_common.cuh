@@ -118,8 +118,8 @@ struct fqeb_graph {
   // ordered lists of the strings with orbital icol occupied / empty, built on first use by
   // the column-rotation kernels (rotate.cu): [norb][C(norb-1,nele-1)] / [norb][C(norb-1,nele)]
   int32_t *d_occ[2], *d_unocc[2];
-  // by-string maps zero-padded to a multiple of 16 columns for the sliced contraction (ozaki.cu),
-  // [compressed pair space?][spin], built on first use
+  // by-string source tables of the sliced contraction (ozaki.cu k_source_table), zero-padded to a
+  // multiple of 16 columns, [compressed pair space?][spin], built on first use
   int32_t *d_ozmapT[2][2];
   int32_t *d_pairs_id;     // identity pair list [norb^2][2] = (ij, -1)
   int32_t *d_rowmap_id;    // identity row map [norb^2]

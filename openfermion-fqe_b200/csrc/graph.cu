@@ -336,9 +336,10 @@ extern "C" int fqeb_graph_destroy(fqeb_graph *g) {
     if (g->d_unocc[s]) cudaFree(g->d_unocc[s]);
     if (g->d_clistT[s]) cudaFree(g->d_clistT[s]);
     if (g->d_clist[s]) cudaFree(g->d_clist[s]);
+  }
+  for (int s = 0; s < 2; ++s)   // always one table per spin (the row lengths differ)
     for (int y = 0; y < 2; ++y)
       if (g->d_ozmapT[y][s]) cudaFree(g->d_ozmapT[y][s]);
-  }
   for (int s = 0; s < 2; ++s) free(g->h_Z[s]);
   if (g->sync) {
     GraphSync *sy = static_cast<GraphSync *>(g->sync);

@@ -22,24 +22,27 @@
 // sigma.cu therefore takes this path only when  127^-6 * max|C| * sqrt(ndet) / ||C||  is below
 // a threshold and the FP64 DMMA kernels otherwise (both are parity-tested).
 //
-// Kernel anatomy (one persistent CTA per SM, 17 warps):
+// Kernel anatomy (one persistent CTA per SM, role-specialised warps; see k_sigma_ozaki2):
 //   * the digit planes of the operand A (B operand of the MMA: N = pairs kl, K = pairs ij) are
 //     copied once per CTA into shared memory in the canonical K-major no-swizzle UMMA layout;
-//   * per tile (one alpha row x 64 beta strings = 128 real rows m = (det, re|im)), 16 worker
+//   * per tile (8 alpha rows x 8 beta strings = 128 real rows m = (det, re|im)), 12 producer
 //     warps gather the 8-byte digit words of the alpha and the beta source of every (m, ij) from
-//     the pre-sliced coefficient planes, add them as packed biased bytes, transpose 4 x 4 bytes
-//     with PRMT and store 16-byte core-matrix rows of the D^T tile (A operand: M = 128, K = ij);
-//   * ONE thread issues the 21 x K/32 tcgen05.mma kind::i8 instructions of the tile, diagonal by
-//     diagonal (d = i + j) into three rotating 144-column accumulators in TMEM;
-//   * the same 16 warps drain the accumulators two diagonals at a time (acc_d * 127 + acc_{d+1}
-//     fits int32), convert to FP64, apply the weights and stream E out, overlapped with the MMAs
-//     of the following diagonals.
+//     the pre-sliced coefficient planes (stored twice, [a][b] and [b][a], so that both gathers of
+//     a warp are short contiguous segments), add them as packed biased bytes, transpose 4 x 4
+//     bytes with PRMT and store 16-byte core-matrix rows of the D^T tile into a staging buffer;
+//   * ONE thread copies the staging buffer into TMEM (tcgen05.cp) and issues the 21 x K/32
+//     tcgen05.mma kind::i8 instructions of the tile per 48-column block, A operand from TMEM,
+//     diagonal by diagonal (d = i + j), one accumulator slot per diagonal in TMEM;
+//   * 8 drain warps fold the accumulators two diagonals at a time (acc_d * 127 + acc_{d+1} fits
+//     int32), convert to FP64, apply the weights and stream E out.
+// Producers, tensor core and drain work on different tiles at the same time.
 #include "fqeb_common.cuh"
 
 #include <math.h>
 #include <string.h>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace fqeb {
@@ -48,12 +51,8 @@ constexpr int OZ_NS = 6;           // digit slices of C and of the operand
 constexpr int OZ_DMAX = 5;         // slice products (i, j) with i + j <= OZ_DMAX are kept
 constexpr int OZ_RADIX = 127;
 constexpr int OZ_NMAX = 136;       // largest pair space (MMA N and K) whose tile + operand image fit in shared memory
-constexpr int OZ_SLOT = 144;       // TMEM columns per accumulator slot
-constexpr int OZ_WORKERS = 512;    // 16 worker warps: producers, then epilogue
-constexpr int OZ_THREADS = OZ_WORKERS + 128;   // + one warpgroup: MMA issuer (3 warps idle)
-constexpr int OZ_TILE_DETS = 64;   // determinants per tile (128 real rows)
 constexpr int OZ_NPROD = (OZ_DMAX + 1) * (OZ_DMAX + 2) / 2;   // 21 slice products
-constexpr int OZ_MAX_MMAS = OZ_NPROD * 5;                     // x K steps (<= 5)
+constexpr uint32_t OZ_NONE = 0xFFFFFFFFu;                     // source table entry: no source
 
 // ---------------------------------------------------------------------------------------
 // coefficient digit planes
@@ -182,15 +181,18 @@ __global__ void __launch_bounds__(256) k_slice_coeff(int64_t lena, int64_t lenb,
   }
 }
 
-// zero-padded copy of a by-string map: dst[x][0..kpad) = src[x][0..np), 0 beyond
-__global__ void k_pad_map(int64_t len, int np, int kpad, const int32_t *__restrict__ src,
-                          int32_t *__restrict__ dst) {
+// source table of a by-string map: dst[x][k] = element index (in 16-byte elements, the negated
+// planes behind the plain ones) of the first element of the source ROW of pair k acting on string
+// x, or OZ_NONE; zero-padded to kpad columns.  The kernel adds the column and loads.
+__global__ void k_source_table(int64_t len, int np, int kpad, uint32_t row_len, uint32_t ndet,
+                               const int32_t *__restrict__ src, uint32_t *__restrict__ dst) {
   const int64_t n = len * kpad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t x = i / kpad;
     const int k = (int)(i - x * kpad);
-    dst[i] = k < np ? src[x * np + k] : 0;
+    const int t = k < np ? src[x * np + k] : 0;
+    dst[i] = t == 0 ? OZ_NONE : (t < 0 ? ndet : 0u) + (uint32_t)(abs(t) - 1) * row_len;
   }
 }
 
@@ -311,12 +313,14 @@ __device__ __forceinline__ uint32_t oz_smem_u32(const void *p) {
 __device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// wait for a phase; the suspend-time hint lets the thread sleep in hardware until the phase
+// completes instead of polling (polling warps were 30 % of the producers' issue slots)
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred P1;\nOZ_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra OZ_DONE;\nbra OZ_WAIT;\nOZ_DONE:\n}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)
       : "memory");
 }
 __device__ __forceinline__ void oz_mbar_arrive(uint32_t bar) {
@@ -353,14 +357,18 @@ __device__ __forceinline__ uint64_t oz_ldg64_if(bool pred, const uint64_t *p, ui
                : "l"(p), "r"((int)pred));
   return v;
 }
-// predicated 16-byte load of four map entries, zeros when off
-__device__ __forceinline__ void oz_ldg128_if(bool pred, const int *p, int &x, int &y, int &z,
-                                             int &w) {
-  x = y = z = w = 0;
+// predicated 16-byte load of four source-table entries, OZ_NONE when off
+__device__ __forceinline__ void oz_ldg128_if(bool pred, const uint32_t *p, uint32_t &x,
+                                             uint32_t &y, uint32_t &z, uint32_t &w) {
+  x = y = z = w = OZ_NONE;
   asm volatile(
-      "{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];\n}"
+      "{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
       : "+r"(x), "+r"(y), "+r"(z), "+r"(w)
       : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void oz_prefetch_l2_if(bool pred, const void *p) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %1, 0;\n @q prefetch.global.L2 [%0];\n}" ::"l"(p),
+               "r"((int)pred));
 }
 __device__ __forceinline__ int oz_ldg32_if(bool pred, const int *p) {
   int v = 0;
@@ -393,7 +401,7 @@ __device__ __forceinline__ int oz_ldg32(const int *p) {
                : "r"(addr))
 
 // ---------------------------------------------------------------------------------------
-// the kernel
+// kernel parameters
 // ---------------------------------------------------------------------------------------
 struct OzParams {
   const int8_t *img;        // operand digit image (global)
@@ -402,8 +410,8 @@ struct OzParams {
   const uint64_t *planes;   // coefficient digit planes [sign][a][b][part]
   const uint64_t *planesT;  // the same, transposed:     [sign][b][a][part]
   int64_t ndet;
-  const int32_t *mapT_a;    // [lena][kpad]  alpha adjoint map by string, zero-padded to kpad = 16 kc
-  const int32_t *mapT_b;    // [lenb][kpad]  beta adjoint map by string
+  const uint32_t *srcT_a;   // [lena][kpad]  alpha source table by string (k_source_table), kpad = 16 kc
+  const uint32_t *srcT_b;   // [lenb][kpad]  beta source table by string
   int kpad;
   int64_t lena, lenb, row0, nrows;
   int pitch, tiles_per_row;
@@ -415,61 +423,101 @@ struct OzParams {
   unsigned long long *prof; // optional [8] cycle counters summed over CTAs (FQEB_OZAKI_PROF=1)
 };
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p) {
+// ---------------------------------------------------------------------------------------
+// the kernel, second generation: role-specialised warps and the tile's MMA copy in TMEM
+// ---------------------------------------------------------------------------------------
+// The tile (110 KB) and the operand image (117 KB) fill shared memory, so the tile cannot be
+// double-buffered there and the first-generation kernel above runs produce -> MMA -> drain ->
+// store strictly one after the other (profiles/r02_ozaki_v1_cycle_profile.txt: 39 k cycles per
+// tile for 8 k cycles of tensor work).  Here the shared-memory tile is only a STAGING buffer:
+//   * 12 producer warps gather tile k+1 into it while the tensor core works on tile k;
+//   * the MMA thread copies it into TMEM (54 x tcgen05.cp.128x128b, ordered with the MMAs in the
+//     tensor pipe, so the write-after-read hazard on the TMEM copy needs no barrier), signals
+//     "staging free" with a commit, and issues the 21 slice products with the A operand read
+//     from TMEM (checked in profiles/microbench/i8_tmem_a.cu), per column block of N = 48,
+//     diagonal d into accumulator slot d;
+//   * 8 drain warps fold the accumulators two diagonals at a time into FP64 running sums (24 per
+//     thread: the block width is set by the drain's register budget - it must not spill, see
+//     below - and by TMEM, which holds six 48-column slots next to the tile) and stream E out;
+//     a slot pair is released as soon as it has been read, so the MMAs of the next block overlap
+//     the drain of this one.
+// TMEM: columns [0, 224) tile, [224, 512) accumulator slots.
+// Register budget: a CTA's setmaxnreg pool is what the launch allocated, and the allocation is
+// per four warps - 24 warps x 80 registers = 61440.  The issuer warpgroup (one working warp)
+// releases down to 24, producers take 88 and drain warps 96 (one octet of gathered digit words
+// in flight per producer thread, source entries two octets ahead; 24 running FP64 sums per drain
+// thread).  Neither role may spill: local memory shares the load/store queue with the producers'
+// gathers, and a spill reload in the drain was measured waiting behind hundreds of them.
+// Twelve producer warps: the SM's load queue returns in issue order, so what hides the latency of
+// the gathers is the number of warps with an octet in flight, not the depth per warp (8 warps
+// with two octets each were measured 2.2x slower than 12 warps with one).
+constexpr int OZ2_PRODUCERS = 384;                 // warpgroups 0-2
+constexpr int OZ2_DRAINERS = 256;                  // warpgroups 3-4
+constexpr int OZ2_THREADS = OZ2_PRODUCERS + OZ2_DRAINERS + 128;   // + warpgroup 5: MMA issuer
+constexpr int OZ2_W_DRAIN = OZ2_PRODUCERS / 32, OZ2_W_ISSUE = (OZ2_PRODUCERS + OZ2_DRAINERS) / 32;
+constexpr int OZ2_A_COLS = 224;
+constexpr int OZ2_NB = 48;                         // columns of a block = MMA N = slot width
+constexpr int OZ2_NSLOT = OZ_DMAX + 1;             // one accumulator slot per diagonal
+
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}"
+               : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void oz_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
+// PROF: in-kernel cycle counters (FQEB_OZAKI_PROF=1); compiled out of the production instance,
+// where the 64-bit counters would cost the producers ten registers
+template <bool PROF>
+__device__ __forceinline__ long long oz_clock() {
+  if constexpr (PROF) return clock64();
+  return 0;
+}
+// KC: number of 16-byte K columns of the pair space (9 at norb = 16, 7 at norb = 14 with
+// real-orbital integrals) as a compile-time constant, or 0 for "any".  With KC known the
+// producers' octet pipeline is straight-line code; inside a run-time loop ptxas tracks every
+// load that is in flight across the back edge with ONE scoreboard, so waiting for the oldest
+// octet waits for everything and nothing overlaps (seen in the SASS control codes).
+template <bool PROF, int KC>
+__global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_bar[8];
+  // 0: staging full, 1: staging free, then per accumulator slot: full (6), free (6)
+  __shared__ __align__(8) uint64_t s_bar[2 + 2 * OZ2_NSLOT];
   __shared__ uint32_t s_tmem;
-  // (A descriptor, B descriptor) of every MMA of a tile, in issue order: loop-invariant, so the
-  // single issuing thread only loads 16 bytes and fires (a dependent ALU chain per MMA was
-  // measured at 175 cycles per MMA, 2.4x the 72-cycle tensor time of a 128 x 144 x 32 step)
-  __shared__ __align__(16) uint4 s_desc[OZ_MAX_MMAS];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kc = p.kc, ng = p.ng;
-  const uint32_t d_bytes = (uint32_t)OZ_NS * kc * 2048;   // D^T tile: [slice][kcol][16 groups][128]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+  const int kc = KC > 0 ? KC : p.kc, ng = p.ng;
+  const uint32_t d_bytes = (uint32_t)OZ_NS * kc * 2048;   // tile: [slice][kcol][16 groups][128]
   uint8_t *s_d = smem;
   uint8_t *s_b = smem + d_bytes;                           // operand image follows the tile
-  const uint32_t bar_dfull = oz_smem_u32(&s_bar[0]), bar_dfree = oz_smem_u32(&s_bar[1]);
-  const uint32_t bar_sfull = oz_smem_u32(&s_bar[2]), bar_sfree = oz_smem_u32(&s_bar[5]);
+  const uint32_t bar_full = oz_smem_u32(&s_bar[0]), bar_free = oz_smem_u32(&s_bar[1]);
+  const uint32_t bar_sfull = oz_smem_u32(&s_bar[2]), bar_sfree = oz_smem_u32(&s_bar[2 + OZ2_NSLOT]);
 
-  // one-time setup: operand image -> shared memory, barriers, TMEM
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
     uint4 *dst = reinterpret_cast<uint4 *>(s_b);
-    for (int i = tid; i < p.img_bytes / 16; i += OZ_THREADS) dst[i] = src[i];
+    for (int i = tid; i < p.img_bytes / 16; i += OZ2_THREADS) dst[i] = src[i];
   }
   if (tid == 0) {
-    oz_mbar_init(bar_dfull, OZ_WORKERS);
-    oz_mbar_init(bar_dfree, 1);
-    for (int s = 0; s < 3; ++s) {
+    oz_mbar_init(bar_full, OZ2_PRODUCERS);
+    oz_mbar_init(bar_free, 1);
+    for (int s = 0; s < OZ2_NSLOT; ++s) {
       oz_mbar_init(bar_sfull + 8 * s, 1);
-      oz_mbar_init(bar_sfree + 8 * s, OZ_WORKERS / 32);
+      oz_mbar_init(bar_sfree + 8 * s, OZ2_DRAINERS / 32);
     }
   }
-  {
-    const uint32_t d_base = oz_smem_u32(s_d), b_base = oz_smem_u32(s_b);
-    const uint32_t b_plane = (uint32_t)kc * ng * 128;
-    const uint32_t zero_base = b_base + OZ_NS * b_plane;
-    const int ksteps = (kc + 1) / 2;
-    for (int e = tid; e < OZ_NPROD * ksteps; e += OZ_THREADS) {
-      // entry e = (product pr, K step ks); products ordered by diagonal d = i + j, then i
-      const int pr = e / ksteps, ks = e - pr * ksteps;
-      int d = 0, rem = pr;
-      while (rem > d) {
-        rem -= d + 1;
-        ++d;
-      }
-      const int i = rem, j = d - rem;   // D slice i, operand slice j
-      const uint32_t a0 = d_base + (uint32_t)(i * kc + 2 * ks) * 2048;
-      const uint32_t b0 = b_base + (uint32_t)j * b_plane + (uint32_t)(2 * ks) * ng * 128;
-      // second 16-byte K column of the step: the next column, or (odd column count) the zero
-      // block on the operand side, which cancels whatever the tile side reads there
-      const bool tail = (2 * ks + 1 >= kc);
-      const uint64_t ad = oz_desc(a0, 2048, 128);
-      const uint64_t bd = oz_desc(b0, tail ? zero_base - b0 : (uint32_t)ng * 128, 128);
-      s_desc[e] = make_uint4((uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32));
-    }
-  }
-  if (warp == 16) {
+  if (warp == OZ2_W_ISSUE) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         oz_smem_u32(&s_tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -481,76 +529,122 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
   const uint32_t tmem = s_tmem;
   const int64_t my_tiles =
       (int64_t)blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // column blocks of 48 pair-space columns (3 at norb = 16); diagonal d of every block
+  // accumulates in slot d, so a slot is filled once per block
+  const int nblk = (p.np + OZ2_NB - 1) / OZ2_NB;
 
-  if (warp >= 16) {
+  if (warp >= OZ2_W_ISSUE) {
     // ================================ MMA issuer ======================================
-    // this warpgroup hands its registers to the workers (5 warps per scheduler at launch
-    // leave 96 registers per thread; the workers need ~110 for 36 running FP64 sums)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
-    if (warp == 16 && lane == 0) {
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
+    if (warp == OZ2_W_ISSUE) {
+      // the whole warp walks the loop (uniform descriptor arithmetic); one elected lane issues
+      const bool leader = oz_elect_one();
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ2_NB >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
-      const int ksteps = (kc + 1) / 2;
-      long long c_wait_tile = 0, c_wait_slot = 0, c_total = clock64();
+      const uint32_t d_base = oz_smem_u32(s_d), b_base = oz_smem_u32(s_b);
+      const uint32_t b_plane = (uint32_t)kc * ng * 128, b_kstep = 2u * ng * 128;
+      const uint32_t zero_base = b_base + OZ_NS * b_plane;
+      const int kfull = kc / 2, ncp = OZ_NS * kc;
+      // descriptor words (K-major, no swizzle, version 1): low = address >> 4 | LBO >> 4 << 16,
+      // high = SBO >> 4 | 1 << 14 with SBO = 128
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t lbo_full = (((uint32_t)ng * 128u) >> 4) << 16;
+      const uint32_t d_lo0 = ((d_base & 0x3FFFF) >> 4) | ((2048u >> 4) << 16);
+      long long c_wait_tile = 0, c_wait_slot = 0, c_total = oz_clock<PROF>();
       for (int64_t it = 0; it < my_tiles; ++it) {
-        long long c0 = clock64();
-        oz_mbar_wait(bar_dfull, (uint32_t)(it & 1));
-        c_wait_tile += clock64() - c0;
+        long long c0 = oz_clock<PROF>();
+        oz_mbar_wait(bar_full, (uint32_t)(it & 1));
+        c_wait_tile += oz_clock<PROF>() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int e = 0;
-#pragma unroll 1
-        for (int d = 0; d <= OZ_DMAX; ++d) {
-          const int slot = d % 3;
-          const int64_t use = 2 * it + d / 3;      // how often this slot has been filled before
-          if (use >= 1) {
-            const long long c1 = clock64();
-            oz_mbar_wait(bar_sfree + 8 * slot, (uint32_t)((use - 1) & 1));
-            c_wait_slot += clock64() - c1;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) {
+          // staging -> TMEM, one 16-byte K column (128 rows x 128 bits) per copy; descriptors are
+          // advanced by plain adds (a dependent chain of descriptor arithmetic per instruction
+          // was measured at ~80 cycles per MMA, twice the tensor time of an N = 80 step)
+          uint32_t lo = d_lo0, ta = tmem;
+#pragma unroll 2
+          for (int c = 0; c < ncp; ++c) {
+            oz_cp_128x128b(ta, ((uint64_t)desc_hi << 32) | lo);
+            lo += 2048u >> 4;
+            ta += 4;
           }
-          const uint32_t acc = tmem + (uint32_t)(slot * OZ_SLOT);
-          const int e_end = e + (d + 1) * ksteps;
-          uint4 cur = s_desc[e];
-          uint32_t first = 0;
-#pragma unroll 1
-          for (; e < e_end; ++e) {
-            const uint4 nxt = s_desc[e + 1 < OZ_MAX_MMAS ? e + 1 : e];   // prefetch
-            oz_mma(acc, (uint64_t)cur.x | ((uint64_t)cur.y << 32),
-                   (uint64_t)cur.z | ((uint64_t)cur.w << 32), idesc, first);
-            first = 1;
-            cur = nxt;
-          }
-          oz_commit(bar_sfull + 8 * slot);
+          oz_commit(bar_free);
         }
-        oz_commit(bar_dfree);
+#pragma unroll 1
+        for (int nb = 0; nb < nblk; ++nb) {
+          const uint32_t b_blk = b_base + (uint32_t)nb * (OZ2_NB / 8) * 128;
+#pragma unroll 1
+          for (int d = 0; d <= OZ_DMAX; ++d) {
+            const int slot = d;
+            const int64_t use = nblk * it + nb;   // how often this slot has been filled before
+            if (use >= 1) {
+              const long long c1 = oz_clock<PROF>();
+              oz_mbar_wait(bar_sfree + 8 * slot, (uint32_t)((use - 1) & 1));
+              c_wait_slot += oz_clock<PROF>() - c1;
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            if (leader) {
+              const uint32_t acc = tmem + (uint32_t)(OZ2_A_COLS + slot * OZ2_NB);
+              uint32_t first = 0;
+              uint32_t a_sl = tmem;                                   // D slice i = 0
+              uint32_t b_sl = b_blk + (uint32_t)d * b_plane;          // operand slice j = d
+#pragma unroll 1
+              for (int i = 0; i <= d; ++i) {
+                uint32_t ta = a_sl;
+                uint32_t lo = ((b_sl & 0x3FFFF) >> 4) | lbo_full;
+                if constexpr (KC > 0) {
+#pragma unroll
+                  for (int ks = 0; ks < KC / 2; ++ks) {
+                    oz_mma_ts(acc, ta, ((uint64_t)desc_hi << 32) | lo, idesc, first);
+                    first = 1;
+                    ta += 8;
+                    lo += b_kstep >> 4;
+                  }
+                } else {
+#pragma unroll 1
+                  for (int ks = 0; ks < kfull; ++ks) {
+                    oz_mma_ts(acc, ta, ((uint64_t)desc_hi << 32) | lo, idesc, first);
+                    first = 1;
+                    ta += 8;
+                    lo += b_kstep >> 4;
+                  }
+                }
+                if (kc & 1) {
+                  // odd column count: the second 16-byte K column of the last step is the zero
+                  // block on the operand side, which cancels whatever the tile side holds there
+                  const uint32_t b0 = b_sl + (uint32_t)kfull * b_kstep;
+                  oz_mma_ts(acc, ta,
+                            ((uint64_t)desc_hi << 32) | ((b0 & 0x3FFFF) >> 4) |
+                                ((((zero_base - b0) >> 4) & 0x3FFF) << 16),
+                            idesc, first);
+                  first = 1;
+                }
+                a_sl += 4u * kc;
+                b_sl -= b_plane;
+              }
+              oz_commit(bar_sfull + 8 * slot);
+            }
+            __syncwarp();
+          }
+        }
       }
-      if (p.prof) {   // issuer: total, waiting for the tile, waiting for an accumulator slot
-        atomicAdd(p.prof + 0, (unsigned long long)(clock64() - c_total));
+      if (PROF && p.prof && leader) {
+        atomicAdd(p.prof + 0, (unsigned long long)(oz_clock<PROF>() - c_total));
         atomicAdd(p.prof + 1, (unsigned long long)c_wait_tile);
         atomicAdd(p.prof + 2, (unsigned long long)c_wait_slot);
         atomicAdd(p.prof + 7, 1ull);
       }
     }
-  } else {
-    // ====================== workers: produce the tile, then drain it ===================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
-    // Row m of the tile = (determinant, part) of an 8 x 8 block of determinants (8 alpha rows x
-    // 8 beta columns); the 32 rows of a lane quarter are a 4 x 4 sub-block, so that one warp-wide
-    // gather of alpha sources (rows of `planes`, contiguous in b) and one of beta sources (rows of
-    // `planesT`, contiguous in a) each touch four 64-byte segments instead of 16 scattered lines
-    const int m = tid & 127;
-    const int h = tid >> 7;              // K-column phase: columns h, h+4, h+8
-    const int part = m & 1;
-    const int ar = 4 * (m >> 6) + ((m >> 3) & 3), bc = 4 * ((m >> 5) & 1) + ((m >> 1) & 3);
-    const uint64_t *pl = p.planes + part, *plT = p.planesT + part;   // element stride: 2 words
-    const int64_t neg_off = 2 * p.ndet;
-    const uint64_t ZERO = 0x4040404040404040ull;
-    // epilogue geometry: lane quarter q (TMEM lanes 32q..32q+31) and column block cb
-    const int q = warp & 3, cblk = warp >> 2;
-    const int cpb = (p.np + 3) / 4;                 // columns per block (<= 36)
-    const int col0 = cblk * cpb;
-    const int erow = q * 32 + lane;                 // accumulator row handled in the epilogue
+  } else if (warp >= OZ2_W_DRAIN) {
+    // ================================== drain ==========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;\n");
+    
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch (warp % 4)
+    const int ch = (warp - OZ2_W_DRAIN) >> 2;   // column half of a block
+    const int erow = q * 32 + lane;         // accumulator row = (determinant of the 8 x 8 tile, part)
     const int e_ar = 4 * (erow >> 6) + ((erow >> 3) & 3), e_bc = 4 * ((erow >> 5) & 1) + ((erow >> 1) & 3);
+    const int epart = erow & 1;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int64_t e_step = 2 * p.lde;               // doubles between consecutive pair rows of E
     const double st = p.stats[2] * p.op_scale;      // S * T
     double w[3];
     {
@@ -559,167 +653,220 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_sigma_ozaki(const OzParams p)
       w[1] = w[0] * r * r;
       w[2] = w[1] * r * r;
     }
+    long long c_drain = 0, c_store = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int r = (int)(tile / p.tiles_per_row);
       const int bt = (int)(tile - (int64_t)r * p.tiles_per_row);
-      // ---------------- produce ----------------
-      // Octets of 8 pair indices: the 16 digit-word loads of octet o are in flight while the map
-      // entries of octet o+1 are fetched (two 16-byte loads per map), so a thread pays about one
-      // memory round trip per octet.
-      long long c_p0 = clock64();
-      if (it >= 1) oz_mbar_wait(bar_dfree, (uint32_t)((it - 1) & 1));
-      const long long c_p1 = clock64();
-      {
-        const int64_t a_loc = 8 * (int64_t)r + ar, b = 8 * (int64_t)bt + bc;
-        const bool valid = a_loc < p.nrows && b < p.lenb;
-        const int64_t a = p.row0 + (valid ? a_loc : 0), bb = valid ? b : 0;
-        const int32_t *ta_row = p.mapT_a + a * p.kpad, *tb_row = p.mapT_b + bb * p.kpad;
-        const uint64_t *src_a = pl + 2 * bb, *src_b = plT + 2 * a;
-        const int ngroups = h < kc ? (kc - h + 3) / 4 : 0;     // groups h, h+4, h+8 < kc
-        auto load_maps = [&](int o, int (&ta_)[8], int (&tb_)[8]) {
-          const int k0 = 16 * (h + 4 * (o >> 1)) + 8 * (o & 1);
-          oz_ldg128_if(valid, ta_row + k0, ta_[0], ta_[1], ta_[2], ta_[3]);
-          oz_ldg128_if(valid, ta_row + k0 + 4, ta_[4], ta_[5], ta_[6], ta_[7]);
-          oz_ldg128_if(valid, tb_row + k0, tb_[0], tb_[1], tb_[2], tb_[3]);
-          oz_ldg128_if(valid, tb_row + k0 + 4, tb_[4], tb_[5], tb_[6], tb_[7]);
-        };
-        int ta[8], tb[8];
-        if (ngroups > 0) load_maps(0, ta, tb);
-        uint32_t out[OZ_NS][4];
-        for (int o = 0; o < 2 * ngroups; ++o) {
-          uint64_t va[8], vb[8];
+      const int64_t a_loc = 8 * (int64_t)r + e_ar, b = 8 * (int64_t)bt + e_bc;
+      const bool live = a_loc < p.nrows && b < p.lenb;
+      double *ebase = reinterpret_cast<double *>(p.E + (a_loc * p.pitch + b)) + epart;
+      double *eptr = ebase + e_step * (OZ2_NB / 2) * ch;   // first column of this thread
+      int nreal = p.np - (OZ2_NB / 2) * ch;                  // columns left in the pair space
+#pragma unroll 1
+      for (int nb = 0; nb < nblk; ++nb) {
+        constexpr int NCOL = OZ2_NB / 2;                      // 24 columns per thread
+        const long long c_d0 = oz_clock<PROF>();
+        const uint32_t par = (uint32_t)((nblk * it + nb) & 1);
+        double run[NCOL];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            va[u] = oz_ldg64_if(ta[u] != 0, src_a + (ta[u] < 0 ? neg_off : 0) +
-                                                2 * (int64_t)(abs(ta[u]) - 1) * p.lenb, ZERO);
-            vb[u] = oz_ldg64_if(tb[u] != 0, src_b + (tb[u] < 0 ? neg_off : 0) +
-                                                2 * (int64_t)(abs(tb[u]) - 1) * p.lena, ZERO);
-          }
-          int nta[8], ntb[8];
-          if (o + 1 < 2 * ngroups) {
-            load_maps(o + 1, nta, ntb);
-          } else {
+        for (int pr = 0; pr < 3; ++pr) {
+          const int sa = 2 * pr, sb = 2 * pr + 1;
+          oz_mbar_wait(bar_sfull + 8 * sa, par);
+          oz_mbar_wait(bar_sfull + 8 * sb, par);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int u = 0; u < 8; ++u) nta[u] = ntb[u] = 0;
-          }
-          const int half = o & 1;
+          for (int rd = 0; rd < NCOL / 8; ++rd) {
+            uint32_t ra[8], rb[8];
+            const uint32_t col = tmem + lane_addr + (uint32_t)(OZ2_A_COLS + NCOL * ch + 8 * rd);
+            OZ_TMEM_LD8(ra, col + (uint32_t)(sa * OZ2_NB));
+            OZ_TMEM_LD8(rb, col + (uint32_t)(sb * OZ2_NB));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int qd = 0; qd < 2; ++qd) {
-            uint64_t e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)   // signed digit sums, per byte
-              e[u] = (va[4 * qd + u] + vb[4 * qd + u]) ^ 0x8080808080808080ull;
-            // 4 x 4 byte transposes: word s of `out` = slice s of the four k of this quad
-            const uint32_t l0 = (uint32_t)e[0], l1 = (uint32_t)e[1], l2 = (uint32_t)e[2],
-                           l3 = (uint32_t)e[3];
-            const uint32_t h0 = (uint32_t)(e[0] >> 32), h1 = (uint32_t)(e[1] >> 32),
-                           h2 = (uint32_t)(e[2] >> 32), h3 = (uint32_t)(e[3] >> 32);
-            const uint32_t t0 = __byte_perm(l0, l1, 0x5140), t1 = __byte_perm(l2, l3, 0x5140);
-            const uint32_t t2 = __byte_perm(l0, l1, 0x7362), t3 = __byte_perm(l2, l3, 0x7362);
-            const uint32_t t4 = __byte_perm(h0, h1, 0x5140), t5 = __byte_perm(h2, h3, 0x5140);
-            const uint32_t w0 = __byte_perm(t0, t1, 0x5410), w1 = __byte_perm(t0, t1, 0x7632);
-            const uint32_t w2 = __byte_perm(t2, t3, 0x5410), w3 = __byte_perm(t2, t3, 0x7632);
-            const uint32_t w4 = __byte_perm(t4, t5, 0x5410), w5 = __byte_perm(t4, t5, 0x7632);
-            if (half == 0) {
-              out[0][qd] = w0; out[1][qd] = w1; out[2][qd] = w2;
-              out[3][qd] = w3; out[4][qd] = w4; out[5][qd] = w5;
-            } else {
-              out[0][2 + qd] = w0; out[1][2 + qd] = w1; out[2][2 + qd] = w2;
-              out[3][2 + qd] = w3; out[4][2 + qd] = w4; out[5][2 + qd] = w5;
+            for (int c = 0; c < 8; ++c) {
+              // int32 -> double on the FP64 pipe (exact): 2^52 + 2^31 + comb, minus the offset
+              const int comb = (int)ra[c] * OZ_RADIX + (int)rb[c];
+              const double cd = __hiloint2double(0x43300000, comb ^ (int)0x80000000) -
+                                4503601774854144.0;
+              run[8 * rd + c] = pr == 0 ? w[0] * cd : fma(w[pr], cd, run[8 * rd + c]);
             }
           }
-          if (half == 1) {
-            // 16-byte core-matrix rows: conflict-free (32 consecutive rows = 512 contiguous bytes)
-            const int g = h + 4 * (o >> 1);
-            const uint32_t dst =
-                oz_smem_u32(s_d) + (uint32_t)(g * 16 + (m >> 3)) * 128 + (m & 7) * 16;
-#pragma unroll
-            for (int sl = 0; sl < OZ_NS; ++sl)
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(
-                               dst + (uint32_t)(sl * kc) * 2048),
-                           "r"(out[sl][0]), "r"(out[sl][1]), "r"(out[sl][2]), "r"(out[sl][3])
-                           : "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            oz_mbar_arrive(bar_sfree + 8 * sa);
+            oz_mbar_arrive(bar_sfree + 8 * sb);
           }
+        }
+        const long long c_d1 = oz_clock<PROF>();
+        // E[kl][a_loc * pitch + b].{re,im}: consecutive lanes of a row segment -> consecutive doubles
+        if (live) {
+          double *ptr = eptr;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            ta[u] = nta[u];
-            tb[u] = ntb[u];
+          for (int c = 0; c < NCOL; ++c) {
+#ifndef OZ_EXP_NOSTORE   // timing experiments only (results are wrong with any OZ_EXP_* macro)
+            if (c < nreal) __stcs(ptr, run[c]);
+#else
+            if (c < nreal && run[c] == 1.2345e300) __stcs(ptr, run[c]);
+#endif
+            ptr += e_step;
+          }
+        }
+        eptr += e_step * OZ2_NB;
+        nreal -= OZ2_NB;
+        c_drain += c_d1 - c_d0;
+        c_store += oz_clock<PROF>() - c_d1;
+      }
+    }
+    if (PROF && p.prof && tid == OZ2_PRODUCERS) {
+      atomicAdd(p.prof + 5, (unsigned long long)c_drain);
+      atomicAdd(p.prof + 6, (unsigned long long)c_store);
+    }
+  } else {
+    // ================================= producers =======================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
+    // Row m of the tile = (determinant, part) of an 8 x 8 block of determinants (8 alpha rows x
+    // 8 beta columns); the 32 rows of a lane quarter are a 4 x 4 sub-block, so that one warp-wide
+    // gather of alpha sources (rows of `planes`, contiguous in b) and one of beta sources (rows of
+    // `planesT`, contiguous in a) each touch four 64-byte segments
+    const int m = tid & 127;
+    const int h = tid >> 7;              // which third of the tile's 2 kc octets (8 pair indices)
+    const int part = m & 1;
+    const int ar = 4 * (m >> 6) + ((m >> 3) & 3), bc = 4 * ((m >> 5) & 1) + ((m >> 1) & 3);
+    const uint64_t *pl = p.planes + part, *plT = p.planesT + part;   // element stride: 2 words
+    const uint64_t ZERO = 0x4040404040404040ull;
+    // octets of this thread: K column o >> 1, half o & 1
+    const int o0 = (2 * kc * h) / 3, o1 = (2 * kc * (h + 1)) / 3;
+    const uint32_t dst0 = oz_smem_u32(s_d) + (uint32_t)(m >> 3) * 128 + (m & 7) * 16;
+    long long c_wait = 0, c_prod = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int r = (int)(tile / p.tiles_per_row);
+      const int bt = (int)(tile - (int64_t)r * p.tiles_per_row);
+      const int64_t a_loc = 8 * (int64_t)r + ar, b = 8 * (int64_t)bt + bc;
+      const bool valid = a_loc < p.nrows && b < p.lenb;
+      const uint32_t a = (uint32_t)(p.row0 + (valid ? a_loc : 0)), bb = valid ? (uint32_t)b : 0u;
+      const uint32_t *ta_row = p.srcT_a + (int64_t)a * p.kpad, *tb_row = p.srcT_b + (int64_t)bb * p.kpad;
+      // source-table entries of 8 pair indices (two 16-byte loads per spin); OZ_NONE when off
+      auto load_srcs = [&](int k0, uint32_t (&ta_)[8], uint32_t (&tb_)[8]) {
+        oz_ldg128_if(valid, ta_row + k0, ta_[0], ta_[1], ta_[2], ta_[3]);
+        oz_ldg128_if(valid, ta_row + k0 + 4, ta_[4], ta_[5], ta_[6], ta_[7]);
+        oz_ldg128_if(valid, tb_row + k0, tb_[0], tb_[1], tb_[2], tb_[3]);
+        oz_ldg128_if(valid, tb_row + k0 + 4, tb_[4], tb_[5], tb_[6], tb_[7]);
+      };
+      // the 16 digit words of an octet: alpha sources are rows of `planes` (+ column b), beta
+      // sources rows of `planesT` (+ column a)
+      auto load_digits = [&](const uint32_t (&ta_)[8], const uint32_t (&tb_)[8], uint64_t (&va)[8],
+                             uint64_t (&vb)[8]) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#if defined(OZ_EXP_NOLOAD)
+          va[u] = ZERO + ta_[u];
+          vb[u] = ZERO + tb_[u];
+#elif defined(OZ_EXP_NOALPHA)
+          va[u] = ZERO + ta_[u];
+          vb[u] = oz_ldg64_if(tb_[u] != OZ_NONE, plT + 2 * (uint64_t)(tb_[u] + a), ZERO);
+#elif defined(OZ_EXP_NOBETA)
+          va[u] = oz_ldg64_if(ta_[u] != OZ_NONE, pl + 2 * (uint64_t)(ta_[u] + bb), ZERO);
+          vb[u] = ZERO + tb_[u];
+#else
+          va[u] = oz_ldg64_if(ta_[u] != OZ_NONE, pl + 2 * (uint64_t)(ta_[u] + bb), ZERO);
+          vb[u] = oz_ldg64_if(tb_[u] != OZ_NONE, plT + 2 * (uint64_t)(tb_[u] + a), ZERO);
+#endif
+        }
+      };
+      // signed digit sums of an octet, 4 x 4 byte transposes (word s of a quad = slice s of its
+      // four k), stored as the 8-byte half `half` of the 16-byte core-matrix rows of K column g
+      auto combine_store = [&](const uint64_t (&va)[8], const uint64_t (&vb)[8], const int g,
+                               const int half) {
+        uint32_t out[OZ_NS][2];
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          uint64_t e[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            e[u] = (va[4 * qd + u] + vb[4 * qd + u]) ^ 0x8080808080808080ull;
+          const uint32_t l0 = (uint32_t)e[0], l1 = (uint32_t)e[1], l2 = (uint32_t)e[2],
+                         l3 = (uint32_t)e[3];
+          const uint32_t h0 = (uint32_t)(e[0] >> 32), h1 = (uint32_t)(e[1] >> 32),
+                         h2 = (uint32_t)(e[2] >> 32), h3 = (uint32_t)(e[3] >> 32);
+          const uint32_t t0 = __byte_perm(l0, l1, 0x5140), t1 = __byte_perm(l2, l3, 0x5140);
+          const uint32_t t2 = __byte_perm(l0, l1, 0x7362), t3 = __byte_perm(l2, l3, 0x7362);
+          const uint32_t t4 = __byte_perm(h0, h1, 0x5140), t5 = __byte_perm(h2, h3, 0x5140);
+          out[0][qd] = __byte_perm(t0, t1, 0x5410);
+          out[1][qd] = __byte_perm(t0, t1, 0x7632);
+          out[2][qd] = __byte_perm(t2, t3, 0x5410);
+          out[3][qd] = __byte_perm(t2, t3, 0x7632);
+          out[4][qd] = __byte_perm(t4, t5, 0x5410);
+          out[5][qd] = __byte_perm(t4, t5, 0x7632);
+        }
+        const uint32_t dst = dst0 + (uint32_t)g * 2048 + 8u * half;
+#pragma unroll
+        for (int sl = 0; sl < OZ_NS; ++sl)
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + (uint32_t)(sl * kc) * 2048),
+                       "r"(out[sl][0]), "r"(out[sl][1])
+                       : "memory");
+      };
+      // Two octets of digit words in flight and source entries fetched two octets ahead: while
+      // octet o is being combined, the digits of o+1 and the sources of o+2 are on their way, so
+      // neither the table nor the plane latency is exposed per octet.  The loads of the first
+      // octets are issued BEFORE waiting for the staging buffer, so they overlap the copy of the
+      // previous tile into TMEM.
+      const long long c_p0 = oz_clock<PROF>();
+      if constexpr (KC > 0) {
+        constexpr int NOCT = (2 * KC + 2) / 3;   // octets per thread (the last one may be absent)
+        uint32_t sa[2][8], sb[2][8];
+        uint64_t va[8], vb[8];
+        load_srcs(8 * o0, sa[0], sb[0]);
+        if (NOCT > 1) load_srcs(8 * (o0 + 1), sa[1], sb[1]);
+#pragma unroll
+        for (int j = 0; j < NOCT; ++j) {
+          // here: sa[j&1] = sources of octet j, sa[(j+1)&1] = sources of j+1 (on their way)
+          const bool on = (2 * KC) % 3 == 0 || j + 1 < NOCT || o0 + j < o1;
+          if (on) load_digits(sa[j & 1], sb[j & 1], va, vb);
+          if (j + 2 < NOCT && o0 + j + 2 < o1) load_srcs(8 * (o0 + j + 2), sa[j & 1], sb[j & 1]);
+          if (j == 0) {
+            // first store of this tile: the staging buffer must have been copied out
+            const long long c_w = oz_clock<PROF>();
+            if (it >= 1) oz_mbar_wait(bar_free, (uint32_t)((it - 1) & 1));
+            c_wait += oz_clock<PROF>() - c_w;
+          }
+          if (on) combine_store(va, vb, (o0 + j) >> 1, (o0 + j) & 1);
+        }
+      } else {
+        // any K-column count: one octet in flight per thread, sources one octet ahead
+        uint32_t ta[8], tb[8], sa[8], sb[8];
+        uint64_t va[8], vb[8];
+        load_srcs(8 * o0, ta, tb);
+#pragma unroll 1
+        for (int o = o0; o < o1; o += 2) {
+          load_digits(ta, tb, va, vb);
+          if (o + 1 < o1) load_srcs(8 * (o + 1), sa, sb);
+          if (o == o0) {
+            const long long c_w = oz_clock<PROF>();
+            if (it >= 1) oz_mbar_wait(bar_free, (uint32_t)((it - 1) & 1));
+            c_wait += oz_clock<PROF>() - c_w;
+          }
+          combine_store(va, vb, o >> 1, o & 1);
+          if (o + 1 < o1) {
+            load_digits(sa, sb, va, vb);
+            if (o + 2 < o1) load_srcs(8 * (o + 2), ta, tb);
+            combine_store(va, vb, (o + 1) >> 1, (o + 1) & 1);
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      oz_mbar_arrive(bar_dfull);
-      const long long c_p2 = clock64();
-      // ---------------- drain ----------------
-      double run[36];
-#pragma unroll
-      for (int c = 0; c < 36; ++c) run[c] = 0.0;
-#pragma unroll
-      for (int pr = 0; pr < 3; ++pr) {
-        const int sa = (2 * pr) % 3, sb = (2 * pr + 1) % 3;
-        const int64_t ua = 2 * it + (2 * pr) / 3, ub = 2 * it + (2 * pr + 1) / 3;
-        oz_mbar_wait(bar_sfull + 8 * sa, (uint32_t)(ua & 1));
-        oz_mbar_wait(bar_sfull + 8 * sb, (uint32_t)(ub & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        // 36 columns per thread in rounds of 8, 8, 8, 8, 4 (small register footprint next to
-        // the 36 running sums)
-#pragma unroll
-        for (int rd = 0; rd < 5; ++rd) {
-          uint32_t ra[8], rb[8];
-          const uint32_t ca = tmem + lane_addr + (uint32_t)(sa * OZ_SLOT + col0 + 8 * rd);
-          const uint32_t cbb = tmem + lane_addr + (uint32_t)(sb * OZ_SLOT + col0 + 8 * rd);
-          if (rd < 4) {
-            OZ_TMEM_LD8(ra, ca);
-            OZ_TMEM_LD8(rb, cbb);
-          } else {
-            OZ_TMEM_LD4(ra, ca);
-            OZ_TMEM_LD4(rb, cbb);
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int c = 0; c < (rd < 4 ? 8 : 4); ++c) {
-            // int32 -> double on the FP64 pipe (exact): 2^52 + 2^31 + comb, minus the offset
-            // (I2F.F64 runs on the quarter-rate conversion unit)
-            const int comb = (int)ra[c] * OZ_RADIX + (int)rb[c];
-            const double cd = __hiloint2double(0x43300000, comb ^ (int)0x80000000) -
-                              4503601774854144.0;
-            run[8 * rd + c] = fma(w[pr], cd, run[8 * rd + c]);
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          oz_mbar_arrive(bar_sfree + 8 * sa);
-          oz_mbar_arrive(bar_sfree + 8 * sb);
-        }
-      }
-      const long long c_p3 = clock64();
-      // E[kl][r*pitch + b].{re,im}: row erow = (det, part); consecutive lanes -> consecutive doubles
-      {
-        const int epart = erow & 1;
-        const int64_t a_loc = 8 * (int64_t)r + e_ar, b = 8 * (int64_t)bt + e_bc;
-        if (a_loc < p.nrows && b < p.lenb) {
-          double *base = reinterpret_cast<double *>(p.E + (a_loc * p.pitch + b)) + epart;
-#pragma unroll
-          for (int c = 0; c < 36; ++c) {
-            const int kl = col0 + c;
-            if (c < cpb && kl < p.np) __stcs(base + 2 * (int64_t)kl * p.lde, run[c]);
-          }
-        }
-      }
-      if (p.prof && tid == 0) {   // worker 0: wait for the tile buffer, produce, drain, store
-        atomicAdd(p.prof + 3, (unsigned long long)(c_p1 - c_p0));
-        atomicAdd(p.prof + 4, (unsigned long long)(c_p2 - c_p1));
-        atomicAdd(p.prof + 5, (unsigned long long)(c_p3 - c_p2));
-        atomicAdd(p.prof + 6, (unsigned long long)(clock64() - c_p3));
-      }
+      oz_mbar_arrive(bar_full);
+      c_prod += oz_clock<PROF>() - c_p0;
+    }
+    if (PROF && p.prof && tid == 0) {
+      atomicAdd(p.prof + 3, (unsigned long long)c_wait);
+      atomicAdd(p.prof + 4, (unsigned long long)(c_prod - c_wait));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 16)
+  if (warp == OZ2_W_ISSUE)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
@@ -784,26 +931,31 @@ double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq) {
 
 static unsigned long long *g_oz_prof = nullptr;
 
-// by-string adjoint maps zero-padded to kpad columns (built once per graph and pair-space kind)
-static int ozaki_maps(const fqeb_graph *g, bool sym, int np, int kpad, const int32_t **ma,
-                      const int32_t **mb) {
+// source tables of both spins (built once per graph and pair-space kind): alpha sources are rows
+// of `planes` (length lenb), beta sources rows of `planesT` (length lena)
+static int ozaki_maps(const fqeb_graph *g, bool sym, int np, int kpad, const uint32_t **ma,
+                      const uint32_t **mb) {
   GraphLock lock(g);
   fqeb_graph *gm = const_cast<fqeb_graph *>(g);
-  const int nspin = g->shared_spin ? 1 : 2;
-  for (int sp = 0; sp < nspin; ++sp) {
+  const int64_t ndet = g->len[0] * g->len[1];
+  FQEB_REQUIRE(2 * ndet + g->len[0] + g->len[1] < (1ll << 32),
+               "ozaki: sector too large for 32-bit source indices");
+  for (int sp = 0; sp < 2; ++sp) {
     if (gm->d_ozmapT[sym][sp]) continue;
     const int64_t len = g->len[sp];
-    int32_t *dst = nullptr;
-    FQEB_CUDA(cudaMalloc(&dst, sizeof(int32_t) * (size_t)len * kpad));
+    uint32_t *dst = nullptr;
+    FQEB_CUDA(cudaMalloc(&dst, sizeof(uint32_t) * (size_t)len * kpad));
     int64_t blocks = (len * kpad + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_pad_map<<<(unsigned)blocks, 256>>>(len, np, kpad, sym ? g->d_smapT[sp] : g->d_amapT[sp], dst);
+    k_source_table<<<(unsigned)blocks, 256>>>(len, np, kpad, (uint32_t)g->len[1 - sp],
+                                              (uint32_t)ndet,
+                                              sym ? g->d_smapT[sp] : g->d_amapT[sp], dst);
     FQEB_CHECK_LAUNCH();
     FQEB_CUDA(cudaDeviceSynchronize());
-    gm->d_ozmapT[sym][sp] = dst;
+    gm->d_ozmapT[sym][sp] = (int32_t *)dst;
   }
-  *ma = gm->d_ozmapT[sym][0];
-  *mb = gm->d_ozmapT[sym][g->shared_spin ? 0 : 1];
+  *ma = (const uint32_t *)gm->d_ozmapT[sym][0];
+  *mb = (const uint32_t *)gm->d_ozmapT[sym][1];
   return FQEB_OK;
 }
 
@@ -826,7 +978,7 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   p.planes = (const uint64_t *)d_planes;
   p.planesT = p.planes + 4 * p.ndet;
   p.kpad = 16 * o.kc;
-  rc = ozaki_maps(g, op->sym, op->np, p.kpad, &p.mapT_a, &p.mapT_b);
+  rc = ozaki_maps(g, op->sym, op->np, p.kpad, &p.srcT_a, &p.srcT_b);
   if (rc != FQEB_OK) return rc;
   p.lena = g->len[0];
   p.lenb = g->len[1];
@@ -854,18 +1006,41 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   // and the last slice's odd K column read)
   // (the odd K column of the last slice reads one 2048-byte column past the tile, i.e. the start
   // of the image: keep at least that much behind the tile for tiny pair spaces)
-  const size_t smem = (size_t)OZ_NS * o.kc * 2048 + (o.img_bytes > 2048 ? o.img_bytes : 2048);
+  // (the kernel multiplies whole column blocks of 48 operand rows: for small pair spaces the
+  // rows past the image must still be addressable shared memory)
+  const size_t smem = (size_t)OZ_NS * o.kc * 2048 + (o.img_bytes > 2048 ? o.img_bytes : 2048) +
+                      (o.np < 128 ? 4096 : 0);
   FQEB_REQUIRE(smem + 1856 <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
   static size_t attr_bytes = 0;   // dynamic + static shared memory must stay within 227 KB
   if (smem > attr_bytes) {
-    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<false, 0>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<false, 7>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<false, 9>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<true, 0>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<true, 7>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<true, 9>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   int64_t grid = sm_count();
   if (grid > p.ntiles) grid = p.ntiles;
   if (grid < 1) return FQEB_OK;
-  k_sigma_ozaki<<<(unsigned)grid, OZ_THREADS, smem, st>>>(p);
+#define OZ_LAUNCH(PROF, KC) k_sigma_ozaki2<PROF, KC><<<(unsigned)grid, OZ2_THREADS, smem, st>>>(p)
+  if (p.prof) {
+    if (p.kc == 9) OZ_LAUNCH(true, 9);
+    else if (p.kc == 7) OZ_LAUNCH(true, 7);
+    else OZ_LAUNCH(true, 0);
+  } else {
+    if (p.kc == 9) OZ_LAUNCH(false, 9);
+    else if (p.kc == 7) OZ_LAUNCH(false, 7);
+    else OZ_LAUNCH(false, 0);
+  }
+#undef OZ_LAUNCH
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
 }

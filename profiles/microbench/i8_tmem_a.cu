@@ -175,7 +175,8 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) uint64_t s_bd[64];
   constexpr int KB = 160;   // 10 K columns of 16 bytes
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   uint8_t *sa = smem, *sb = smem + 6 * M * KB;
   for (int i = tid; i < 6 * M * KB + n * KB; i += blockDim.x) smem[i] = (uint8_t)((i * 37 + 11) & 0x3f);
   if (tid == 0)
@@ -191,7 +192,13 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 1) {
+    // the whole warp walks the loop (descriptor arithmetic in the uniform datapath), one
+    // elected lane issues: with a single-thread branch ptxas wraps every tcgen05 instruction
+    // in R2UR moves and an ELECT loop (~117 cycles per MMA whatever the shape)
+    uint32_t is_leader;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(is_leader));
+    const bool leader = is_leader != 0;
     const uint32_t idesc = make_idesc(n, 0, 1);
     const uint32_t acc0 = tmem + 224;
     uint64_t adv[5];
@@ -202,26 +209,36 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
     for (int it = 0; it < iters; ++it) {
       const int slot = it & 1;
       if (it >= 2) mbar_wait(smem_u32(&bar[slot]), (uint32_t)((it / 2 - 1) & 1));
+      if (leader) {
       if (what == 2 || what == 3) {
         for (int c = 0; c < 54; ++c)
           tmem_cp_128x128b(tmem + 4 * c, make_desc(smem_u32(sa) + c * (M / 8) * 128, (M / 8) * 128, 128));
       }
       if (what != 2) {
+        // descriptors advance by plain adds in (uniform) registers: the issue loop must not be
+        // the limit (a smem-table / ALU-chain loop was measured at 138 cycles per MMA)
         const uint32_t acc = acc0 + (uint32_t)(slot * n);
+        const uint64_t bd0 = make_desc(smem_u32(sb), (n / 8) * 128, 128);
+        const uint32_t bstep = (2u * (n / 8) * 128) >> 4;
         for (int c = 0; c < nchain; c += 5) {
+          uint64_t bd = bd0;
+          uint32_t ta = tmem + 40 * ((c / 5) % 5);
 #pragma unroll
           for (int ks = 0; ks < 5; ++ks) {
-            const uint64_t bd = s_bd[ks];
             if (what == 1) umma_i8_ss(acc, adv[ks], bd, idesc, (c + ks) > 0);
-            else umma_i8_ts(acc, tmem + 8 * ks + 40 * ((c / 5) % 5), bd, idesc, (c + ks) > 0);
+            else umma_i8_ts(acc, ta, bd, idesc, (c + ks) > 0);
+            bd += bstep;
+            ta += 8;
           }
         }
       }
       umma_commit(smem_u32(&bar[slot]));
+      }
+      __syncwarp();
     }
     for (int it = (iters > 2 ? iters - 2 : 0); it < iters; ++it)
       mbar_wait(smem_u32(&bar[it & 1]), (uint32_t)((it / 2) & 1));
-    cycles[blockIdx.x] = clock64() - t0;
+    if (leader) cycles[blockIdx.x] = clock64() - t0;
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -390,8 +407,9 @@ int main() {
   if (!ok) printf("CORRECTNESS FAILED somewhere - see above\n");
   const int sms = prop.multiProcessorCount;
   for (int what : {0, 1}) {
-    for (int n : {64, 80, 144}) run_rate(what, n, 105, 500, sms);
+    for (int n : {32, 48, 64, 80, 144}) run_rate(what, n, 105, 500, sms);
   }
+  run_rate(0, 48, 315, 500, sms);
   run_rate(0, 80, 210, 500, sms);
   run_rate(2, 80, 105, 500, sms);
   run_rate(3, 80, 210, 500, sms);

@@ -34,11 +34,11 @@ lib.fqeb_ozaki_profile(prof)
 ntiles = ((d.lena() + 7) // 8) * ((d.lenb() + 7) // 8) * reps   # 8 x 8 determinant tiles (chunk edges ignored)
 print(f"norb={norb} path={lib.fqeb_sigma_last_path()} sigma {dt*1e3:.1f} ms; phases per sigma (ms): "
       f"prepass {ms3[0]/reps:.2f} contract {ms3[1]/reps:.2f} scatter {ms3[2]/reps:.2f}; launches {list(cnt3)}")
-names = ["issuer total", "issuer wait tile", "issuer wait slot", "worker wait buffer", "worker produce",
-         "worker drain", "worker store"]
+names = ["issuer total", "issuer wait tile", "issuer wait slot", "producer wait staging", "producer produce",
+         "drain (incl. waiting for MMAs)", "drain store"]
 nctas = prof[7]
 if nctas:
     tiles_per_cta = ntiles / nctas
     for i, nm in enumerate(names):
-        print(f"  {nm:20s} {prof[i]/nctas/tiles_per_cta:10.0f} cycles per tile per CTA")
+        print(f"  {nm:32s} {prof[i]/nctas/tiles_per_cta:10.0f} cycles per tile per CTA")
     print(f"  ({nctas} CTA launches, {tiles_per_cta:.1f} tiles per CTA)")
