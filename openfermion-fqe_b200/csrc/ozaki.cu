@@ -181,18 +181,25 @@ __global__ void __launch_bounds__(256) k_slice_coeff(int64_t lena, int64_t lenb,
   }
 }
 
-// source table of a by-string map: dst[x][k] = element index (in 16-byte elements, the negated
-// planes behind the plain ones) of the first element of the source ROW of pair k acting on string
-// x, or OZ_NONE; zero-padded to kpad columns.  The kernel adds the column and loads.
+// source table of a by-string map: the entry of (string x, pair k) = element index (in 16-byte
+// elements, the negated planes behind the plain ones) of the first element of the source ROW of
+// pair k acting on x, or OZ_NONE; the kernel adds the column and loads.  Layout: octets of 8
+// consecutive k, the octets of 4 consecutive strings adjacent,
+//     dst[(((x >> 2) * (kpad / 8) + (k >> 3)) * 4 + (x & 3)) * 8 + (k & 7)],
+// so that the 16-byte loads of a warp (4 strings, one octet) fall into one 128-byte line.
+__host__ __device__ inline int64_t oz_table_offset(int64_t x, int k, int kpad) {
+  return (((x >> 2) * (kpad >> 3) + (k >> 3)) * 4 + (x & 3)) * 8 + (k & 7);
+}
 __global__ void k_source_table(int64_t len, int np, int kpad, uint32_t row_len, uint32_t ndet,
                                const int32_t *__restrict__ src, uint32_t *__restrict__ dst) {
-  const int64_t n = len * kpad;
+  const int64_t len4 = (len + 3) / 4 * 4, n = len4 * kpad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t x = i / kpad;
     const int k = (int)(i - x * kpad);
-    const int t = k < np ? src[x * np + k] : 0;
-    dst[i] = t == 0 ? OZ_NONE : (t < 0 ? ndet : 0u) + (uint32_t)(abs(t) - 1) * row_len;
+    const int t = (x < len && k < np) ? src[x * np + k] : 0;
+    dst[oz_table_offset(x, k, kpad)] =
+        t == 0 ? OZ_NONE : (t < 0 ? ndet : 0u) + (uint32_t)(abs(t) - 1) * row_len;
   }
 }
 
@@ -410,8 +417,8 @@ struct OzParams {
   const uint64_t *planes;   // coefficient digit planes [sign][a][b][part]
   const uint64_t *planesT;  // the same, transposed:     [sign][b][a][part]
   int64_t ndet;
-  const uint32_t *srcT_a;   // [lena][kpad]  alpha source table by string (k_source_table), kpad = 16 kc
-  const uint32_t *srcT_b;   // [lenb][kpad]  beta source table by string
+  const uint32_t *srcT_a;   // alpha source table by string (k_source_table layout), kpad = 16 kc
+  const uint32_t *srcT_b;   // beta source table by string
   int kpad;
   int64_t lena, lenb, row0, nrows;
   int pitch, tiles_per_row;
@@ -641,7 +648,9 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch (warp % 4)
     const int ch = (warp - OZ2_W_DRAIN) >> 2;   // column half of a block
     const int erow = q * 32 + lane;         // accumulator row = (determinant of the 8 x 8 tile, part)
-    const int e_ar = 4 * (erow >> 6) + ((erow >> 3) & 3), e_bc = 4 * ((erow >> 5) & 1) + ((erow >> 1) & 3);
+    // tile row = 16 ar + 2 bc + part: the 32 rows of a lane quarter are 2 alpha rows x 8 beta
+    // columns x (re, im), so a warp-wide store of one pair row of E is two full 128-byte lines
+    const int e_ar = erow >> 4, e_bc = (erow >> 1) & 7;
     const int epart = erow & 1;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int64_t e_step = 2 * p.lde;               // doubles between consecutive pair rows of E
@@ -725,14 +734,16 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
   } else {
     // ================================= producers =======================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
-    // Row m of the tile = (determinant, part) of an 8 x 8 block of determinants (8 alpha rows x
-    // 8 beta columns); the 32 rows of a lane quarter are a 4 x 4 sub-block, so that one warp-wide
-    // gather of alpha sources (rows of `planes`, contiguous in b) and one of beta sources (rows of
-    // `planesT`, contiguous in a) each touch four 64-byte segments
-    const int m = tid & 127;
+    // A tile is an 8 x 8 block of determinants (8 alpha rows x 8 beta columns) x (re, im).  The 32
+    // threads of a producer warp take a 4 x 4 sub-block, so that one warp-wide gather of alpha
+    // sources (rows of `planes`, contiguous in b) and one of beta sources (rows of `planesT`,
+    // contiguous in a) each touch four 64-byte segments; the tile ROW they fill is chosen for the
+    // drain (16 ar + 2 bc + part, see there).
+    const int mt = tid & 127;
     const int h = tid >> 7;              // which third of the tile's 2 kc octets (8 pair indices)
-    const int part = m & 1;
-    const int ar = 4 * (m >> 6) + ((m >> 3) & 3), bc = 4 * ((m >> 5) & 1) + ((m >> 1) & 3);
+    const int part = mt & 1;
+    const int ar = 4 * (mt >> 6) + ((mt >> 3) & 3), bc = 4 * ((mt >> 5) & 1) + ((mt >> 1) & 3);
+    const int m = 16 * ar + 2 * bc + part;
     const uint64_t *pl = p.planes + part, *plT = p.planesT + part;   // element stride: 2 words
     const uint64_t ZERO = 0x4040404040404040ull;
     // octets of this thread: K column o >> 1, half o & 1
@@ -746,13 +757,16 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
       const int64_t a_loc = 8 * (int64_t)r + ar, b = 8 * (int64_t)bt + bc;
       const bool valid = a_loc < p.nrows && b < p.lenb;
       const uint32_t a = (uint32_t)(p.row0 + (valid ? a_loc : 0)), bb = valid ? (uint32_t)b : 0u;
-      const uint32_t *ta_row = p.srcT_a + (int64_t)a * p.kpad, *tb_row = p.srcT_b + (int64_t)bb * p.kpad;
+      // octet o of string x: 8 entries at oz_table_offset(x, 8 o, kpad); 32 entries per octet step
+      const uint32_t *ta_row = p.srcT_a + oz_table_offset(a, 0, p.kpad);
+      const uint32_t *tb_row = p.srcT_b + oz_table_offset(bb, 0, p.kpad);
       // source-table entries of 8 pair indices (two 16-byte loads per spin); OZ_NONE when off
       auto load_srcs = [&](int k0, uint32_t (&ta_)[8], uint32_t (&tb_)[8]) {
-        oz_ldg128_if(valid, ta_row + k0, ta_[0], ta_[1], ta_[2], ta_[3]);
-        oz_ldg128_if(valid, ta_row + k0 + 4, ta_[4], ta_[5], ta_[6], ta_[7]);
-        oz_ldg128_if(valid, tb_row + k0, tb_[0], tb_[1], tb_[2], tb_[3]);
-        oz_ldg128_if(valid, tb_row + k0 + 4, tb_[4], tb_[5], tb_[6], tb_[7]);
+        const int ofs = 4 * k0;   // (k0 / 8) octets x 32 entries
+        oz_ldg128_if(valid, ta_row + ofs, ta_[0], ta_[1], ta_[2], ta_[3]);
+        oz_ldg128_if(valid, ta_row + ofs + 4, ta_[4], ta_[5], ta_[6], ta_[7]);
+        oz_ldg128_if(valid, tb_row + ofs, tb_[0], tb_[1], tb_[2], tb_[3]);
+        oz_ldg128_if(valid, tb_row + ofs + 4, tb_[4], tb_[5], tb_[6], tb_[7]);
       };
       // the 16 digit words of an octet: alpha sources are rows of `planes` (+ column b), beta
       // sources rows of `planesT` (+ column a)
@@ -944,8 +958,9 @@ static int ozaki_maps(const fqeb_graph *g, bool sym, int np, int kpad, const uin
     if (gm->d_ozmapT[sym][sp]) continue;
     const int64_t len = g->len[sp];
     uint32_t *dst = nullptr;
-    FQEB_CUDA(cudaMalloc(&dst, sizeof(uint32_t) * (size_t)len * kpad));
-    int64_t blocks = (len * kpad + 255) / 256;
+    const int64_t len4 = (len + 3) / 4 * 4;
+    FQEB_CUDA(cudaMalloc(&dst, sizeof(uint32_t) * (size_t)len4 * kpad));
+    int64_t blocks = (len4 * kpad + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_source_table<<<(unsigned)blocks, 256>>>(len, np, kpad, (uint32_t)g->len[1 - sp],
                                               (uint32_t)ndet,
