@@ -163,6 +163,18 @@ int fqeb_gemm_col_align(void);
  * nij must be zero-filled by the caller). */
 int fqeb_contract_dvec_rows(const fqeb_op *op, int nij);
 
+/* f4  G[m, n] += sum_c conj(bra[m, c]) * ket[n, c]     (reduction over determinants, FP64 DMMA)
+ * replaces the contractions of FqeData.rdm12 / rdm1 (fqe_data.py:1726-1838, 1668-1724:
+ * numpy.tensordot / einsum of dvec.conj() with dvec over the determinant indices), where bra and
+ * ket are D = E_ij C blocks from fqeb_make_dvec.  d_bra: [M][ldb], d_ket: [N][ldk] complex128,
+ * d_G: row-major [M][N] complex128, accumulated into (caller zero-fills).  When d_ket_last is not
+ * NULL, row N-1 of ket is taken from there (ncols contiguous elements): passing the coefficient
+ * block itself yields <D[ij] | C>, the one-particle part, in the same pass.  Split over column
+ * slabs with a fixed-order second pass: bitwise reproducible, no atomics. */
+int fqeb_gram_accumulate(int M, int N, int64_t ncols, const double *d_bra, int64_t ldb,
+                         const double *d_ket, int64_t ldk, const double *d_ket_last,
+                         double *d_G, void *stream);
+
 /* ------------------------------------------------------------------------
  * a5/a6  sigma = (h1', h2') applied to C        FqeData.apply_inplace((h1,h2))
  * replaces FqeData._apply_array_spatial12 (fqe_data.py:582-608, 644-710) and the

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "fqe_b200", "lib")
 OUT = os.path.join(OUT_DIR, "libfqe_b200.so")
 SOURCES = ["core.cu", "graph.cu", "blas1.cu", "dcoulomb.cu", "dvec.cu", "dgemm.cu", "sigma.cu",
-           "rotate.cu", "nbody.cu", "ozaki.cu"]
+           "rotate.cu", "nbody.cu", "ozaki.cu", "rdm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

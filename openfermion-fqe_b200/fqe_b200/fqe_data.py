@@ -620,8 +620,10 @@ class FqeData:
 
     def _rdm_blocks(self, bradata: Optional['FqeData'], want2: bool):
         """sum over alpha-row blocks of  T[ij] = <D_bra[ij] | C>  and  G[ij,kl] =
-        <D_bra[ij] | D_ket[kl]>, D = E_ij applied to the state (gather kernel); the two small
-        reductions over the determinant index are library GEMMs (cuBLAS through torch)."""
+        <D_bra[ij] | D_ket[kl]>, D = E_ij applied to the state (gather kernel).  Both reductions
+        over the determinant index run in one pass of the library's split-K FP64 tensor-core
+        kernel (csrc/rdm.cu, ``fqeb_gram_accumulate``): the coefficient block rides along as an
+        extra ket row, so T is the last column of the accumulated matrix."""
         dev = _require_cuda()
         bra = self if bradata is None else bradata
         if bra.lena() != self.lena() or bra.lenb() != self.lenb() or bra.norb() != self.norb():
@@ -630,27 +632,30 @@ class FqeData:
         npair = norb * norb
         # two D blocks of at most _rdm_block_bytes (4 GB) each
         rows = max(1, min(la, self._rdm_block_bytes // max(1, 16 * npair * lb)))
-        t1 = torch.zeros(npair, dtype=torch.complex128, device=dev)
-        g2 = torch.zeros((npair, npair), dtype=torch.complex128, device=dev) if want2 else None
+        ncol = npair + 1 if want2 else 1
+        acc = torch.zeros((npair, ncol), dtype=torch.complex128, device=dev)
         ket_c, bra_c = self._check_coeff(self.coeff), self._check_coeff(bra.coeff)
         for r0 in range(0, la, rows):
             nr = min(rows, la - r0)
             ld = nr * lb
-            dket = torch.empty((npair, ld), dtype=torch.complex128, device=dev)
-            _lib.call("fqeb_make_dvec", self._core.handle, ket_c.data_ptr(), dket.data_ptr(), ld,
-                      r0, nr, 0, npair, _stream())
+            dket = None
+            if want2 or bra is self:
+                dket = torch.empty((npair, ld), dtype=torch.complex128, device=dev)
+                _lib.call("fqeb_make_dvec", self._core.handle, ket_c.data_ptr(), dket.data_ptr(),
+                          ld, r0, nr, 0, npair, _stream())
             if bra is self:
                 dbra = dket
             else:
                 dbra = torch.empty((npair, ld), dtype=torch.complex128, device=dev)
                 _lib.call("fqeb_make_dvec", self._core.handle, bra_c.data_ptr(), dbra.data_ptr(),
                           ld, r0, nr, 0, npair, _stream())
-            t1 += dbra.conj() @ ket_c[r0:r0 + nr].reshape(-1)
-            if want2:
-                g2 += dbra.conj() @ dket.transpose(0, 1)
+            _lib.call("fqeb_gram_accumulate", npair, ncol, ld, dbra.data_ptr(), ld,
+                      dket.data_ptr() if want2 else None, ld,
+                      ket_c.data_ptr() + 16 * r0 * lb, acc.data_ptr(), _stream())
             del dket, dbra
-        return t1.cpu().numpy().reshape(norb, norb), \
-            (g2.cpu().numpy().reshape((norb,) * 4) if want2 else None)
+        acc = acc.cpu().numpy()
+        return numpy.ascontiguousarray(acc[:, ncol - 1]).reshape(norb, norb), \
+            (numpy.ascontiguousarray(acc[:, :npair]).reshape((norb,) * 4) if want2 else None)
 
     def rdm1(self, bradata: Optional['FqeData'] = None) -> Tuple[numpy.ndarray]:
         """(rdm1,) with rdm1[i,j] = <bra| a+_i a_j |ket>, spin-summed (fqe_data.py:1668-1724)"""

@@ -61,6 +61,8 @@ SIGNATURES = {
     "fqeb_contract": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int,
                               c_int, c_void_p]),
     "fqeb_gemm_col_align": (c_int, []),
+    "fqeb_gram_accumulate": (c_int, [c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                     c_void_p, c_void_p, c_void_p]),
     "fqeb_contract_dvec_rows": (c_int, [c_void_p, c_int]),
     "fqeb_sigma_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_int64, c_int, c_int]),
     "fqeb_sigma_rows_for_workspace": (c_int64, [c_void_p, c_void_p, c_size_t, c_int, c_int]),

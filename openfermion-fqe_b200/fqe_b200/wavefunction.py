@@ -619,8 +619,38 @@ class Wavefunction:
             sec.evolve_diagonal_coulomb(diag, vij, inplace=True)
         return self
 
-    def expectationValue(self, ops, brawfn: Optional['Wavefunction'] = None) -> complex:
-        """<bra|H|self> via one sigma build and one dot product
-        (wavefunction.py:1100-1133, Hamiltonian branch)."""
+    def expectationValue(self, ops, brawfn: Optional['Wavefunction'] = None):
+        """<bra|H|self> via one sigma build and one dot product, or - for an operator string -
+        an element (indices given as digits, openfermion convention) or a whole tensor (letters)
+        of expectation values (wavefunction.py:1100-1133)."""
+        if isinstance(ops, str):
+            if any(ch.isdigit() for ch in ops):
+                ops = sparse_hamiltonian.SparseHamiltonian(ops)
+            else:
+                return self.rdm(ops, brawfn=brawfn)
+        if not isinstance(ops, hamiltonian.Hamiltonian):
+            raise TypeError('Expected an Fqe Hamiltonian or Operator'
+                            ' but recieved {}'.format(type(ops)))
         bra = brawfn if brawfn is not None else self
         return bra.vdot(self.apply(ops))
+
+    def rdm(self, string: str, brawfn: Optional['Wavefunction'] = None):
+        """Expectation values of the operator string (wavefunction.py:1331-1355): with digits
+        (``'0^ 2'``, spin orbitals) one number <bra| op |self>; with letters (``'i^ j k l^'``) the
+        spin-summed tensor over all spatial orbitals, assembled from the particle RDMs of the
+        device path by Wick reordering (fqe_b200/wick.py)."""
+        if any(ch.isdigit() for ch in string):
+            result = self.apply(sparse_hamiltonian.SparseHamiltonian(string))
+            return (self if brawfn is None else brawfn).vdot(result)
+        tokens = string.split()
+        if len(tokens) % 2 or not tokens:
+            raise ValueError("an operator string needs an even number of operators")
+        ncre = sum(1 for t in tokens if len(t) == 2 and t[0].islower() and t[1] == '^')
+        nann = sum(1 for t in tokens if len(t) == 1 and t.islower())
+        if ncre + nann != len(tokens):
+            raise TypeError("Unsupported behavior for {}".format(string))
+        if ncre != nann:
+            raise ValueError("operator string does not conserve the particle number")
+        from fqe_b200.wick import wick
+        rank = len(tokens) // 2
+        return wick(string, list(self._compute_rdm(rank, brawfn)), True)

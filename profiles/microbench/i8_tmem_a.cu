@@ -166,7 +166,9 @@ k_check(const uint8_t *__restrict__ a, const int8_t *__restrict__ b, int n, int 
 }
 
 // rates.  what = 0: TS MMAs (A in TMEM), 1: SS MMAs, 2: 54 tcgen05.cp.128x128b + commit per
-// iteration, 3: like 0 but every iteration is preceded by the 54 copies (the real per-tile order)
+// iteration, 3: like 0 but every iteration is preceded by the 54 copies (the real per-tile order),
+// 4: like 0 but consecutive MMAs alternate between two accumulators (is the fixed cost per MMA a
+// read-after-write bubble on the accumulator?)
 __global__ void __launch_bounds__(128, 1)
 k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
        int32_t *__restrict__ sink) {
@@ -226,6 +228,8 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
 #pragma unroll
           for (int ks = 0; ks < 5; ++ks) {
             if (what == 1) umma_i8_ss(acc, adv[ks], bd, idesc, (c + ks) > 0);
+            else if (what == 4)   // consecutive MMAs alternate between two accumulators
+              umma_i8_ts(acc0 + (uint32_t)(((c + ks) & 1) * n), ta, bd, idesc, (c + ks) > 1);
             else umma_i8_ts(acc, ta, bd, idesc, (c + ks) > 0);
             bd += bstep;
             ta += 8;
@@ -385,7 +389,8 @@ static void run_rate(int what, int n, int nchain, int iters, int sms) {
   CHECK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
   long long mx = 0;
   for (auto c : h) mx = c > mx ? c : mx;
-  const char *names[] = {"TS (A in TMEM)", "SS (A in smem)", "54 x cp.128x128b only", "54 x cp + TS MMAs"};
+  const char *names[] = {"TS (A in TMEM)", "SS (A in smem)", "54 x cp.128x128b only", "54 x cp + TS MMAs",
+                         "TS, alternating accs"};
   printf("rate  %-22s N=%3d  %3d MMAs/iter x %4d : %8.1f cycles/iter  %6.1f cycles/MMA (tensor floor %5.1f)\n",
          names[what], n, what == 2 ? 0 : nchain, iters, (double)mx / iters,
          what == 2 ? 0.0 : (double)mx / iters / nchain, 128.0 * n / 256.0);
@@ -409,6 +414,8 @@ int main() {
   for (int what : {0, 1}) {
     for (int n : {32, 48, 64, 80, 144}) run_rate(what, n, 105, 500, sms);
   }
+  for (int n : {48, 72, 144}) run_rate(4, n, 105, 500, sms);
+  run_rate(0, 72, 210, 500, sms);
   run_rate(0, 48, 315, 500, sms);
   run_rate(0, 80, 210, 500, sms);
   run_rate(2, 80, 105, 500, sms);

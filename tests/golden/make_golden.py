@@ -27,6 +27,8 @@ Outputs (all small, committed):
     ref_nbody.npz               SURVEY 8f rank 2: individual n-body apply / exact evolution through
                                 FqeData and through Wavefunction + SparseHamiltonian (`--only nbody`)
     ref_rdm.npz                 SURVEY 8f rank 4: FqeData.rdm1 / rdm12, plain and transition (`--only rdm`)
+    ref_wick.npz                Wavefunction.rdm / expectationValue with operator strings, every
+                                spin-free rank-1 / rank-2 ordering (`--only wick`)
     ref_wfn_save.bin / .npz     a file written by the reference's Wavefunction.save and its
                                 coefficients (`--only wfnio`)
 """
@@ -286,6 +288,33 @@ def wfnio_goldens(fqe):
     print("ref_wfn_save.bin", os.path.getsize(os.path.join(HERE, "ref_wfn_save.bin")), "bytes")
 
 
+def wick_goldens(fqe):
+    """Wavefunction.rdm / expectationValue with operator strings (wavefunction.py:1331-1355,
+    1100-1133; wick.py): every spin-free rank-1 and rank-2 ordering the reference accepts, plain
+    and transition (single elements given by digits need openfermion's parser in the reference
+    and are checked against these tensors instead)."""
+    out = {}
+    strings = ["i^ j", "i j^", "j^ i", "i^ j^ k l", "i^ j k l^", "i j^ k^ l", "i j k^ l^",
+               "k^ l^ i j", "p^ q r s^"]
+    out["strings"] = np.array(strings)
+    for tag, n, sz, norb in [("wa", 4, 0, 4), ("wb", 3, 1, 5), ("wc", 2, 0, 3)]:
+        rng = np.random.default_rng(20261000 + 100 * norb + ord(tag[1]))
+        wfn = fqe.Wavefunction([[n, sz, norb]])
+        shape = wfn.get_coeff((n, sz)).shape
+        ket, bra = rand_state(shape, rng), rand_state(shape, rng)
+        wfn.set_wfn(strategy="from_data", raw_data={(n, sz): ket.copy()})
+        bwfn = fqe.Wavefunction([[n, sz, norb]])
+        bwfn.set_wfn(strategy="from_data", raw_data={(n, sz): bra.copy()})
+        out[f"{tag}_meta"] = np.array([n, sz, norb], dtype=np.int64)
+        out[f"{tag}_ket"], out[f"{tag}_bra"] = ket, bra
+        for k, st in enumerate(strings):
+            out[f"{tag}_s{k}"] = np.asarray(wfn.rdm(st))
+            out[f"{tag}_t{k}"] = np.asarray(wfn.rdm(st, brawfn=bwfn))
+            out[f"{tag}_e{k}"] = np.asarray(wfn.expectationValue(st, brawfn=bwfn))
+    np.savez_compressed(os.path.join(HERE, "ref_wick.npz"), **out)
+    print("ref_wick.npz", os.path.getsize(os.path.join(HERE, "ref_wick.npz")), "bytes")
+
+
 def main():
     src = build_reference()
     install_stubs()
@@ -298,7 +327,7 @@ def main():
     fqe.settings.use_accelerated_code = True
     if "--only" in sys.argv:
         {"transform": transform_goldens, "nbody": nbody_goldens, "rdm": rdm_goldens,
-         "wfnio": wfnio_goldens}[
+         "wfnio": wfnio_goldens, "wick": wick_goldens}[
             sys.argv[sys.argv.index("--only") + 1]](fqe)
         return
 

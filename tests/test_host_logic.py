@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: Hamiltonian containers, electron counting,
 shard arithmetic, synthetic inputs."""
+import os
 import numpy as np
 import pytest
 
@@ -192,3 +193,34 @@ def test_rotation_factors_match_oracle_and_reconstruct():
         _, l2, u2, mat2 = rotation_factors(back, low, upp)
         assert l2 is low and u2 is upp
         assert np.allclose(mat2, O.column_operator(low, upp), atol=1e-13)
+
+
+def test_wick_reordering_matches_reference(golden_dir):
+    """fqe_b200.wick against the reference's Wavefunction.rdm outputs (tests/golden/ref_wick.npz,
+    generated by make_golden.py --only wick): every string is rebuilt from the two particle RDMs
+    the same file holds ('i^ j' and 'i^ j^ k l')."""
+    from fqe_b200.wick import wick
+    g = np.load(os.path.join(golden_dir, "ref_wick.npz"))
+    strings = [str(s) for s in g["strings"]]
+    for tag in ("wa", "wb", "wc"):
+        for pre in ("s", "t"):
+            data = [g[f"{tag}_{pre}0"], g[f"{tag}_{pre}3"]]
+            for k, st in enumerate(strings):
+                ref = g[f"{tag}_{pre}{k}"]
+                got = wick(st, data[:len(st.split()) // 2])
+                assert got.shape == ref.shape
+                assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (tag, st)
+
+
+def test_wick_rejects_bad_strings():
+    from fqe_b200.wick import wick
+    r1 = np.zeros((3, 3), dtype=np.complex128)
+    r2 = np.zeros((3,) * 4, dtype=np.complex128)
+    with pytest.raises(ValueError):
+        wick("i^ j^ k^ l", [r1, r2])     # two creators in spin slot 0
+    with pytest.raises(ValueError):
+        wick("i^ jj", [r1])
+    with pytest.raises(ValueError):
+        wick("i^ j k", [r1, r2])
+    with pytest.raises(ValueError):
+        wick("i^ j^ k l", [r1])          # rank-2 string needs rdm2
