@@ -194,6 +194,26 @@ int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
                           void *d_workspace, size_t workspace_bytes,
                           int64_t row0, int64_t row1, int ij0, int ij1,
                           void *stream);
+
+/* The same build with the scatter of the LAST chunk of alpha rows left to the caller, for
+ * multi-GPU runs: fqeb_scatter_rows then completes sigma by slices of TARGET rows [x0, x1), so
+ * that the all-reduce of a finished slice (NCCL, another stream) overlaps the scatter of the
+ * next one.  `pending` describes the deferred launch (the E chunk lives in the workspace, which
+ * must stay untouched until the last slice has been issued); nrows == 0 means nothing was
+ * deferred (one-body operator, empty shard) and fqeb_scatter_rows is a no-op. */
+typedef struct fqeb_pending_scatter {
+  const double *d_evec;      /* E chunk, rows = pair space, in the workspace           */
+  int64_t lde, pitch;        /* complex elements per E row / per alpha row inside it   */
+  int64_t row0, nrows;       /* alpha rows the chunk covers                            */
+  const int32_t *d_rowmap;   /* E row of pair kl                                       */
+  double zr, zi;             /* global factor applied by the scatter                   */
+} fqeb_pending_scatter;
+int fqeb_sigma_restricted_deferred(const fqeb_graph *g, const fqeb_op *op,
+                                   const double *d_coeff, double *d_sigma, void *d_workspace,
+                                   size_t workspace_bytes, int64_t row0, int64_t row1, int ij0,
+                                   int ij1, fqeb_pending_scatter *pending, void *stream);
+int fqeb_scatter_rows(const fqeb_graph *g, const fqeb_pending_scatter *pending, int64_t x0,
+                      int64_t x1, double *d_sigma, void *stream);
 /* Same, HOST buffers in and out (the reference-facing call: numpy coeff in,
  * numpy sigma out; what a maintainer binds at src/fqe/fqe_data.py:685 in place of the three
  * lm_apply_array12_* calls).  Pageable host memory is fine: transfers are staged through a

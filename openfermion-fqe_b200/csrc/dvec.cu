@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kTB, 3)
 k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
              const int2 *__restrict__ clistT_a, const int2 *__restrict__ clist_b,
              const int32_t *__restrict__ rowmap, const double2 *__restrict__ evec, int64_t lde,
-             int64_t pitch, int64_t row0, int64_t nrows, int nbt, double2 z,
+             int64_t pitch, int64_t row0, int64_t nrows, int nbt, int64_t x0, double2 z,
              double2 *__restrict__ out) {
   extern __shared__ int s_mem[];
   int *s_rowmap = s_mem;                                   // [npair]
@@ -285,7 +285,7 @@ k_make_coeff(int npair, int64_t lena, int64_t lenb, int lk_a, int lk_b,
   __shared__ int s_wcount[kTB / 32];
   __shared__ int s_nhit;
   const int64_t tile = blockIdx.x;
-  const int64_t x = tile / nbt;
+  const int64_t x = x0 + tile / nbt;   // target row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int p = threadIdx.x; p < npair; p += kTB) s_rowmap[p] = rowmap[p];
   if (threadIdx.x == 0) s_nhit = 0;
@@ -531,9 +531,10 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
 // rowmap == nullptr: identity (E row kl <-> pair kl)
 // pitch: distance (complex elements) between consecutive alpha rows inside an E row
 // (lenb for the plain layout, a multiple of 64 for the fused kernel's layout)
+// x0 <= x < x1: target rows to complete (the whole sigma: 0, lena)
 int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t pitch,
                       int64_t row0, int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
-                      double *d_out, cudaStream_t st) {
+                      double *d_out, cudaStream_t st, int64_t x0, int64_t x1) {
   if (!d_rowmap) d_rowmap = g->d_rowmap_id;
   const int npair = g->norb * g->norb;
   const int64_t lena = g->len[0], lenb = g->len[1];
@@ -542,17 +543,32 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
                (long long)nrows, (long long)lena);
   FQEB_REQUIRE(pitch >= lenb && lde >= nrows * pitch, "make_coeff: lde=%lld < nrows*pitch",
                (long long)lde);
-  if (nrows == 0 || npair == 0) return FQEB_OK;
+  if (x1 < 0) x1 = lena;
+  FQEB_REQUIRE(x0 >= 0 && x0 <= x1 && x1 <= lena, "make_coeff: target rows [%lld,%lld) invalid",
+               (long long)x0, (long long)x1);
+  if (nrows == 0 || npair == 0 || x0 == x1) return FQEB_OK;
   const int nbt = (int)((lenb + kTB - 1) / kTB);
-  const int64_t tiles = lena * nbt;
+  const int64_t tiles = (x1 - x0) * nbt;
   FQEB_REQUIRE(tiles < (1ll << 31), "make_coeff: problem too large for one launch");
-  const size_t smem = sizeof(int) * (size_t)((npair + 1) & ~1) + sizeof(int2) * (size_t)g->lk[0];
-  if (smem > 48 * 1024)
+  size_t smem = sizeof(int) * (size_t)((npair + 1) & ~1) + sizeof(int2) * (size_t)g->lk[0];
+  {
+    // experiment knob: FQEB_SCATTER_CTAS_PER_SM=k pads the dynamic shared memory so that only k
+    // CTAs fit on an SM (fewer target rows in flight -> smaller beta-way footprint in L2)
+    static const int cap = getenv("FQEB_SCATTER_CTAS_PER_SM") ? atoi(getenv("FQEB_SCATTER_CTAS_PER_SM")) : 0;
+    if (cap >= 1 && cap <= 8) {
+      const size_t pad = (size_t)(227 * 1024) / cap - 2048;
+      if (pad > smem) smem = pad;
+    }
+  }
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
     FQEB_CUDA(cudaFuncSetAttribute(k_make_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
+    attr_smem = smem;
+  }
   k_make_coeff<<<(unsigned)tiles, kTB, smem, st>>>(
       npair, lena, lenb, g->lk[0], g->lk[1], g->d_clistT[0], g->d_clist[1], d_rowmap,
-      (const double2 *)d_evec, lde, pitch, row0, nrows, nbt, make_double2(zr, zi),
+      (const double2 *)d_evec, lde, pitch, row0, nrows, nbt, x0, make_double2(zr, zi),
       (double2 *)d_out);
   FQEB_CHECK_LAUNCH();
   return FQEB_OK;
@@ -577,5 +593,5 @@ extern "C" int fqeb_make_coeff(const fqeb_graph *g, const double *d_evec, int64_
   if (rc != FQEB_OK) return rc;
   FQEB_REQUIRE(g && d_evec && d_out, "fqeb_make_coeff: NULL argument");
   return fqeb::launch_make_coeff(g, d_evec, lde, g->len[1], row0, nrows, nullptr, zr, zi, d_out,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, 0, -1);
 }

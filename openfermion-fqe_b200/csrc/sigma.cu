@@ -25,6 +25,7 @@
 
 #include <string.h>
 #include <map>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <tuple>
@@ -36,7 +37,7 @@ int launch_make_dvec(const fqeb_graph *g, const double *d_coeff, double *d_dvec,
                      int np_eff, const double *d_h1, double *d_sig, cudaStream_t st);
 int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, int64_t pitch,
                       int64_t row0, int64_t nrows, const int32_t *d_rowmap, double zr, double zi,
-                      double *d_out, cudaStream_t st);
+                      double *d_out, cudaStream_t st, int64_t x0 = 0, int64_t x1 = -1);
 int launch_one_body(const fqeb_graph *g, const double *d_coeff, const double *d_h1, int64_t row0,
                     int64_t nrows, double *d_out, cudaStream_t st);
 int launch_fused(const fqeb_graph *g, const fqeb_op *op, const double *d_A, const double *d_coeff,
@@ -182,10 +183,14 @@ extern "C" int64_t fqeb_sigma_rows_for_workspace(const fqeb_graph *g, const fqeb
   return lo;
 }
 
-extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
-                                     const double *d_coeff, double *d_sigma, void *d_workspace,
-                                     size_t workspace_bytes, int64_t row0, int64_t row1, int ij0,
-                                     int ij1, void *stream) {
+// The sigma build.  With `pending` the scatter of the LAST chunk is not launched but described
+// there (fqeb_sigma_restricted_deferred): the caller completes sigma by target-row slices
+// (fqeb_scatter_rows) and can start reducing finished slices across ranks meanwhile.
+static int sigma_build(const fqeb_graph *g, const fqeb_op *op, const double *d_coeff,
+                       double *d_sigma, void *d_workspace, size_t workspace_bytes, int64_t row0,
+                       int64_t row1, int ij0, int ij1, void *stream,
+                       fqeb_pending_scatter *pending) {
+  if (pending) memset(pending, 0, sizeof(*pending));
   int rc = require_device();
   if (rc != FQEB_OK) return rc;
   rc = check_shard(g, op, ij0, ij1);
@@ -258,6 +263,10 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
                                    ij1, st);
       }
       if (rc != FQEB_OK) return rc;
+      if (pending && a0 + rows_chunk >= row1) {
+        *pending = fqeb_pending_scatter{d_e, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi};
+        break;
+      }
       {
         PhaseTimer t(2, st);
         rc = launch_make_coeff(g, d_e, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi,
@@ -297,6 +306,10 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
       rc = launch_contract(op, d_A, d_dvec, L.ldd, d_evec, L.ldd, nr * lenb, ij0, ij1, st);
     }
     if (rc != FQEB_OK) return rc;
+    if (pending && a0 + rows_chunk >= row1) {
+      *pending = fqeb_pending_scatter{d_evec, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi};
+      break;
+    }
     {
       PhaseTimer t(2, st);
       rc = launch_make_coeff(g, d_evec, L.ldd, L.pitch, a0, nr, op->d_rowmap, op->zr, op->zi,
@@ -305,6 +318,36 @@ extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
     if (rc != FQEB_OK) return rc;
   }
   return FQEB_OK;
+}
+
+extern "C" int fqeb_sigma_restricted(const fqeb_graph *g, const fqeb_op *op,
+                                     const double *d_coeff, double *d_sigma, void *d_workspace,
+                                     size_t workspace_bytes, int64_t row0, int64_t row1, int ij0,
+                                     int ij1, void *stream) {
+  return sigma_build(g, op, d_coeff, d_sigma, d_workspace, workspace_bytes, row0, row1, ij0, ij1,
+                     stream, nullptr);
+}
+
+extern "C" int fqeb_sigma_restricted_deferred(const fqeb_graph *g, const fqeb_op *op,
+                                              const double *d_coeff, double *d_sigma,
+                                              void *d_workspace, size_t workspace_bytes,
+                                              int64_t row0, int64_t row1, int ij0, int ij1,
+                                              fqeb_pending_scatter *pending, void *stream) {
+  FQEB_REQUIRE(pending != nullptr, "sigma_deferred: NULL pending descriptor");
+  return sigma_build(g, op, d_coeff, d_sigma, d_workspace, workspace_bytes, row0, row1, ij0, ij1,
+                     stream, pending);
+}
+
+extern "C" int fqeb_scatter_rows(const fqeb_graph *g, const fqeb_pending_scatter *pending,
+                                 int64_t x0, int64_t x1, double *d_sigma, void *stream) {
+  int rc = require_device();
+  if (rc != FQEB_OK) return rc;
+  FQEB_REQUIRE(g && pending && d_sigma, "scatter_rows: NULL argument");
+  if (pending->nrows == 0 || pending->d_evec == nullptr) return FQEB_OK;   // nothing was deferred
+  PhaseTimer t(2, (cudaStream_t)stream);
+  return launch_make_coeff(g, pending->d_evec, pending->lde, pending->pitch, pending->row0,
+                           pending->nrows, pending->d_rowmap, pending->zr, pending->zi, d_sigma,
+                           (cudaStream_t)stream, x0, x1);
 }
 
 // Taylor propagator, whole recurrence on the device (reference wavefunction.py:548-567):
@@ -417,21 +460,87 @@ struct HostCtx {
 std::map<int, HostCtx> g_host_ctx;
 std::mutex g_host_mu;   // the entry point is serialised per process (one workspace per device)
 
+// Host-side copies between the caller's pageable arrays and the pinned staging buffers are what
+// bounds this entry point (2 x 2.65 GB per build at norb = 16): a small persistent pool of copy
+// threads, created on first use, splits every block.
+class CopyPool {
+ public:
+  explicit CopyPool(unsigned n) : nthreads_(n) {
+    for (unsigned t = 0; t < n; ++t) workers_.emplace_back([this, t]() { run(t); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+  }
+  void copy(char *dst, const char *src, size_t n) {
+    std::unique_lock<std::mutex> lock(mu_);
+    dst_ = dst;
+    src_ = src;
+    n_ = n;
+    pending_ = nthreads_;
+    ++epoch_;
+    cv_.notify_all();
+    done_.wait(lock, [this]() { return pending_ == 0; });
+  }
+  unsigned size() const { return nthreads_; }
+
+ private:
+  void run(unsigned t) {
+    uint64_t seen = 0;
+    for (;;) {
+      char *dst;
+      const char *src;
+      size_t n;
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [&]() { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        dst = dst_;
+        src = src_;
+        n = n_;
+      }
+      const size_t per = ((n + nthreads_ - 1) / nthreads_ + 4095) & ~(size_t)4095;
+      const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+      if (lo < hi) memcpy(dst + lo, src + lo, hi - lo);
+      {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  unsigned nthreads_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t n_ = 0;
+  unsigned pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
 void parallel_memcpy(char *dst, const char *src, size_t n) {
-  const size_t kMin = 8u << 20;
-  unsigned nt = n >= 4 * kMin ? 4 : (n >= 2 * kMin ? 2 : 1);
-  if (nt == 1) {
+  if (n < (8u << 20)) {
     memcpy(dst, src, n);
     return;
   }
-  std::vector<std::thread> pool;
-  const size_t per = (n / nt + 63) & ~(size_t)63;
-  for (unsigned t = 0; t < nt; ++t) {
-    const size_t lo = (size_t)t * per, hi = (t + 1 == nt) ? n : ((size_t)(t + 1) * per < n ? (size_t)(t + 1) * per : n);
-    if (lo >= hi) break;
-    pool.emplace_back([=]() { memcpy(dst + lo, src + lo, hi - lo); });
-  }
-  for (auto &th : pool) th.join();
+  // FQEB_COPY_THREADS overrides; default 4 (the copies are bound by host memory bandwidth: more
+  // threads were not faster on the boxes measured, scripts/cabi_host_time.py)
+  static CopyPool *pool = []() {
+    unsigned nt = 4;
+    if (const char *env = getenv("FQEB_COPY_THREADS")) nt = (unsigned)atoi(env);
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    return new CopyPool(nt);   // lives until process exit (workers are blocked on the condition)
+  }();
+  pool->copy(dst, src, n);
 }
 
 // pageable host -> device through the pinned double buffer: the host-side copy of block k+1

@@ -21,6 +21,8 @@ from typing import List, Tuple
 import torch
 import torch.distributed as dist
 
+from fqe_b200 import settings
+
 
 def split_even(total: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
     """Contiguous [lo, hi) slices of range(total) for each rank; every boundary except
@@ -64,8 +66,36 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
         return sector.apply_operator(op)
     rows, pairs = shard_plan(mode, dist.get_rank(), dist.get_world_size(), sector.lena(),
                              op.npair)
-    part = sector.apply_operator(op, row_range=rows, pair_range=pairs)
-    return allreduce_sigma(part)
+    nslices = int(settings.allreduce_slices)
+    if nslices <= 1 or not sector.coeff.is_cuda:
+        part = sector.apply_operator(op, row_range=rows, pair_range=pairs)
+        return allreduce_sigma(part)
+    # The scatter of the last chunk is issued by slices of target rows; the all-reduce of a
+    # finished slice runs on a side stream while the next slice is scattered, so that of the
+    # 2.65 GB reduction (norb = 16) only the last slice's share is exposed.
+    part, pending = sector.apply_operator(op, row_range=rows, pair_range=pairs,
+                                          defer_last_scatter=True)
+    main = torch.cuda.current_stream()
+    side = _side_stream(part.device)
+    flat = torch.view_as_real(part)
+    for x0, x1 in split_even(sector.lena(), nslices):
+        if x1 == x0:
+            continue
+        sector.finish_scatter(pending, x0, x1, part)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dist.all_reduce(flat[x0:x1], op=dist.ReduceOp.SUM)
+    main.wait_stream(side)
+    return part
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    if device not in _SIDE_STREAMS:
+        _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[device]
 
 
 def block_slices(total: int, world: int) -> List[Tuple[int, int]]:

@@ -425,10 +425,13 @@ class FqeData:
             raise NotImplementedError("4-body dense operators are outside the B200 hot path")
 
     def apply_operator(self, op: DenseOperator, row_range=None, pair_range=None,
-                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       out: Optional[torch.Tensor] = None, defer_last_scatter: bool = False):
         """sigma for a prepared operator.  ``row_range`` / ``pair_range`` restrict the
         work to one rank's shard (partial sigma); ``out`` is an optional caller-owned
-        contiguous complex128 [lena, lenb] CUDA tensor that receives the result."""
+        contiguous complex128 [lena, lenb] CUDA tensor that receives the result.
+        With ``defer_last_scatter`` the scatter of the last chunk is left to the caller:
+        returns ``(sigma, pending)`` and ``finish_scatter(pending, x0, x1, sigma)`` completes
+        target rows [x0, x1) (multi-GPU: the all-reduce of finished rows overlaps the rest)."""
         dev = _require_cuda()
         if op.norb != self.norb():
             raise ValueError("operator / wavefunction orbital mismatch")
@@ -448,10 +451,21 @@ class FqeData:
             minimum = int(lib.fqeb_sigma_workspace_bytes(self._core.handle, op.handle, 1, p0, p1))
             ws = _workspace(dev, wanted, minimum, reserve=16 * self._n())
             ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+        if defer_last_scatter:
+            pending = _lib.PendingScatter()
+            _lib.call("fqeb_sigma_restricted_deferred", self._core.handle, op.handle,
+                      self._check_coeff(self.coeff).data_ptr(), sigma.data_ptr(), ws_ptr,
+                      ws_bytes, r0, r1, p0, p1, ctypes.byref(pending), _stream())
+            return sigma, pending
         _lib.call("fqeb_sigma_restricted", self._core.handle, op.handle,
                   self._check_coeff(self.coeff).data_ptr(), sigma.data_ptr(), ws_ptr, ws_bytes,
                   r0, r1, p0, p1, _stream())
         return sigma
+
+    def finish_scatter(self, pending, x0: int, x1: int, sigma: torch.Tensor) -> None:
+        """complete target rows [x0, x1) of a sigma built with ``defer_last_scatter``"""
+        _lib.call("fqeb_scatter_rows", self._core.handle, ctypes.byref(pending), int(x0), int(x1),
+                  self._check_coeff(sigma).data_ptr(), _stream())
 
     def taylor_inplace(self, op: DenseOperator, accuracy: float = 1.0e-15,
                        expansion: int = 30) -> int:
@@ -520,7 +534,7 @@ class FqeData:
         dvec0 = self.calculate_dvec_spatial()                       # [norb, norb, lena, lenb]
         zero_h1 = numpy.zeros((norb, norb), dtype=_C128)
         acc = torch.zeros((npair + 8, ld), dtype=torch.complex128, device=dev)
-        evec = torch.empty_like(acc)
+        evec = torch.zeros_like(acc)     # padding rows and columns are summed into acc too
         dvec2 = None
         for i in range(norb):
             for j in range(norb):

@@ -28,6 +28,12 @@ class FqeB200Error(RuntimeError):
         self.code = code
 
 
+class PendingScatter(ctypes.Structure):
+    """``fqeb_pending_scatter``: the deferred scatter of the last chunk of a sigma build"""
+    _fields_ = [("d_evec", c_void_p), ("lde", c_int64), ("pitch", c_int64), ("row0", c_int64),
+                ("nrows", c_int64), ("d_rowmap", c_void_p), ("zr", c_double), ("zi", c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/fqe_b200.h declares
 SIGNATURES = {
     "fqeb_last_error": (c_char_p, []),
@@ -68,6 +74,11 @@ SIGNATURES = {
     "fqeb_sigma_rows_for_workspace": (c_int64, [c_void_p, c_void_p, c_size_t, c_int, c_int]),
     "fqeb_sigma_restricted": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_int64, c_int64, c_int, c_int, c_void_p]),
+    "fqeb_sigma_restricted_deferred": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_size_t, c_int64, c_int64, c_int, c_int,
+                                               POINTER(PendingScatter), c_void_p]),
+    "fqeb_scatter_rows": (c_int, [c_void_p, POINTER(PendingScatter), c_int64, c_int64, c_void_p,
+                                  c_void_p]),
     "fqeb_sigma_restricted_host": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                            c_void_p]),
     "fqeb_profile_enable": (c_int, [c_int]),

@@ -168,7 +168,8 @@ k_check(const uint8_t *__restrict__ a, const int8_t *__restrict__ b, int n, int 
 // rates.  what = 0: TS MMAs (A in TMEM), 1: SS MMAs, 2: 54 tcgen05.cp.128x128b + commit per
 // iteration, 3: like 0 but every iteration is preceded by the 54 copies (the real per-tile order),
 // 4: like 0 but consecutive MMAs alternate between two accumulators (is the fixed cost per MMA a
-// read-after-write bubble on the accumulator?)
+// read-after-write bubble on the accumulator?), 5: like 0 but TWO warps issue, each nchain MMAs per
+// iteration into its own accumulators (is the fixed cost on the issuing side?)
 __global__ void __launch_bounds__(128, 1)
 k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
        int32_t *__restrict__ sink) {
@@ -194,7 +195,8 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  if (warp == 1) {
+  if (warp == 1 || (what == 5 && warp == 2)) {
+    const int w2 = warp - 1;   // what = 5: two issuing warps, each with its own accumulators
     // the whole warp walks the loop (descriptor arithmetic in the uniform datapath), one
     // elected lane issues: with a single-thread branch ptxas wraps every tcgen05 instruction
     // in R2UR moves and an ELECT loop (~117 cycles per MMA whatever the shape)
@@ -209,7 +211,7 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
       adv[ks] = make_desc(smem_u32(sa) + ks * 2 * (M / 8) * 128, (M / 8) * 128, 128);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
-      const int slot = it & 1;
+      const int slot = (it & 1) + 2 * w2;
       if (it >= 2) mbar_wait(smem_u32(&bar[slot]), (uint32_t)((it / 2 - 1) & 1));
       if (leader) {
       if (what == 2 || what == 3) {
@@ -241,8 +243,8 @@ k_rate(int what, int n, int nchain, int iters, long long *__restrict__ cycles,
       __syncwarp();
     }
     for (int it = (iters > 2 ? iters - 2 : 0); it < iters; ++it)
-      mbar_wait(smem_u32(&bar[it & 1]), (uint32_t)((it / 2) & 1));
-    if (leader) cycles[blockIdx.x] = clock64() - t0;
+      mbar_wait(smem_u32(&bar[(it & 1) + 2 * w2]), (uint32_t)((it / 2) & 1));
+    if (leader) atomicMax((unsigned long long *)&cycles[blockIdx.x], (unsigned long long)(clock64() - t0));
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -382,6 +384,7 @@ static void run_rate(int what, int n, int nchain, int iters, int sms) {
   CHECK(cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_rate<<<sms, 128, smem>>>(what, n, nchain, 4, dcyc, dsink);
   CHECK(cudaDeviceSynchronize());
+  CHECK(cudaMemset(dcyc, 0, sizeof(long long) * sms));
   k_rate<<<sms, 128, smem>>>(what, n, nchain, iters, dcyc, dsink);
   CHECK(cudaGetLastError());
   CHECK(cudaDeviceSynchronize());
@@ -390,10 +393,10 @@ static void run_rate(int what, int n, int nchain, int iters, int sms) {
   long long mx = 0;
   for (auto c : h) mx = c > mx ? c : mx;
   const char *names[] = {"TS (A in TMEM)", "SS (A in smem)", "54 x cp.128x128b only", "54 x cp + TS MMAs",
-                         "TS, alternating accs"};
+                         "TS, alternating accs", "TS, two issuing warps"};
   printf("rate  %-22s N=%3d  %3d MMAs/iter x %4d : %8.1f cycles/iter  %6.1f cycles/MMA (tensor floor %5.1f)\n",
          names[what], n, what == 2 ? 0 : nchain, iters, (double)mx / iters,
-         what == 2 ? 0.0 : (double)mx / iters / nchain, 128.0 * n / 256.0);
+         what == 2 ? 0.0 : (double)mx / iters / (what == 5 ? 2 * nchain : nchain), 128.0 * n / 256.0);
   cudaFree(dcyc);
   cudaFree(dsink);
 }
@@ -414,8 +417,9 @@ int main() {
   for (int what : {0, 1}) {
     for (int n : {32, 48, 64, 80, 144}) run_rate(what, n, 105, 500, sms);
   }
-  for (int n : {48, 72, 144}) run_rate(4, n, 105, 500, sms);
-  run_rate(0, 72, 210, 500, sms);
+  for (int n : {48, 96, 144}) run_rate(4, n, 105, 500, sms);
+  for (int n : {32, 48, 64}) run_rate(5, n, 105, 500, sms);
+  run_rate(0, 96, 105, 500, sms);
   run_rate(0, 48, 315, 500, sms);
   run_rate(0, 80, 210, 500, sms);
   run_rate(2, 80, 105, 500, sms);
