@@ -557,6 +557,13 @@ def run_b200(args):
             traffic = tr["fused"]["dram_bytes_per_launch"] if fused else tr["dram_bytes_per_launch"]
     except Exception:
         pass
+    traffic_sliced = None
+    try:
+        tr2 = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if args.norb == 16 and world == 1 and main["op_sym"] and main["op_kind"] != L.OP_COMPLEX:
+            traffic_sliced = tr2["sliced"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     gemm_s = main["phase_ms"][1] * 1e-3
     launches_per_step = main["phase_launches"][1] // max(args.steps, 1)
     flop_model = "%d*P^2*L^2 with P=%d pairs (%s; %s)" % (
@@ -576,11 +583,14 @@ def run_b200(args):
         ach_i8 = i8_ops * args.steps / gemm_s / 1e12 if gemm_s > 0 else 0.0
         roofline = {
             "bound": "tensor",
-            "kernel": "k_sigma_ozaki (gather of digit planes into the UMMA tile + 21 INT8 slice "
+            "kernel": "k_sigma_ozaki2 (gather of digit planes into the UMMA tile + 21 INT8 slice "
                       "products per tile on tcgen05.mma kind::i8, INT32 accumulators in TMEM, "
                       "FP64 reconstruction in the epilogue; the gather phase is inside this kernel)",
             "achieved": ach_i8, "peak": i8_peak, "unit": "TOP/s",
-            "frac": ach_i8 / i8_peak if i8_peak > 0 else None, "traffic": None,
+            "frac": ach_i8 / i8_peak if i8_peak > 0 else None, "traffic": traffic_sliced,
+            "traffic_unit": "DRAM bytes per launch of the sliced contraction (ncu), see "
+                            "profiles/r02_traffic.json; quoted only for the configuration it was "
+                            "captured on (norb=16, one GPU)",
             "peak_source": "tcgen05.mma kind::i8 M=128 N=256 K=32 on all SMs, CUDA-event timed, "
                            "this run (fqeb_i8_tensor_peak); MEASURED_PEAKS.json has bf16 only",
             "ops_model": "2 * 21 slice products * P^2 * 2*ndet INT8 multiply-adds with P=%d "

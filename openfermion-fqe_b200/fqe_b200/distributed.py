@@ -77,6 +77,7 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
                                           defer_last_scatter=True)
     main = torch.cuda.current_stream()
     side = _side_stream(part.device)
+    group = _reduce_group()
     flat = torch.view_as_real(part)
     for x0, x1 in split_even(sector.lena(), nslices):
         if x1 == x0:
@@ -84,18 +85,37 @@ def sharded_apply(sector, op, mode: str = "det") -> torch.Tensor:
         sector.finish_scatter(pending, x0, x1, part)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            dist.all_reduce(flat[x0:x1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(flat[x0:x1], op=dist.ReduceOp.SUM, group=group)
     main.wait_stream(side)
     return part
 
 
 _SIDE_STREAMS = {}
+_REDUCE_GROUP = []
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
     if device not in _SIDE_STREAMS:
-        _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[device] = torch.cuda.Stream(device=device, priority=-1)
     return _SIDE_STREAMS[device]
+
+
+def _reduce_group():
+    """Process group of the sliced sigma reduction.  The scatter launches thousands of CTAs per
+    SM; a collective kernel on an ordinary stream only gets SMs when that grid has drained, i.e.
+    nothing overlaps.  On NCCL the reduction therefore runs in its own communicator whose
+    stream has HIGH priority, so that its few CTAs are placed ahead of the scatter's pending
+    ones.  (Collective call: every rank reaches it in its first ``sharded_apply``.)"""
+    if not _REDUCE_GROUP:
+        group = dist.group.WORLD
+        if dist.get_backend() == "nccl":
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                group = dist.new_group(backend="nccl", pg_options=opts)
+            except (AttributeError, RuntimeError, TypeError):
+                group = dist.group.WORLD
+        _REDUCE_GROUP.append(group)
+    return _REDUCE_GROUP[0]
 
 
 def block_slices(total: int, world: int) -> List[Tuple[int, int]]:

@@ -37,7 +37,7 @@ operator by at most that amount."""
 
 import os as _os
 
-allreduce_slices = int(_os.environ.get("FQEB_ALLREDUCE_SLICES", "4"))
+allreduce_slices = int(_os.environ.get("FQEB_ALLREDUCE_SLICES", "6"))
 """Multi-GPU sigma (fqe_b200.distributed.sharded_apply): the scatter of a rank's last chunk is
 issued in this many slices of target rows and each finished slice is all-reduced on a side
 stream while the next one is scattered; 1 = one all-reduce after the whole build."""
