@@ -154,8 +154,12 @@ def use_all_host_threads():
     import ctypes
     cores = host_cores()
     os.environ["OMP_NUM_THREADS"] = str(cores)
+    # BLAS (scipy's zaxpy, called inside the OpenMP loops) must not nest its own pthreads.  Do NOT
+    # set MKL_NUM_THREADS here: with an OpenMP-threaded BLAS that variable caps the whole
+    # process's OpenMP team, and the reference's loops then run on ONE thread (measured: cpu
+    # time == wall time) while omp_get_max_threads() still reports all cores.
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    os.environ.pop("MKL_NUM_THREADS", None)
     from oracle import ref_harness as R
     R.lib()                       # loads oracle/_ref/libfqe_ref*.so (and libgomp with it)
     try:
@@ -210,8 +214,10 @@ def run_reference(args):
     R, g, c, h1, h2 = cpu_inputs(args.norb, args.kind)
     # warm-up: a small exact-work slice (loads the library, touches the tables and C)
     R.time_sigma_sample(g, c, h1, h2, 16)
+    import resource
     times = []
     t_begin = time.perf_counter()
+    cpu_begin = resource.getrusage(resource.RUSAGE_SELF)
     sig = None
     while len(times) < max(1, args.steps):
         if times and (time.perf_counter() - t_begin) + times[-1] > args.ref_budget:
@@ -219,6 +225,10 @@ def run_reference(args):
         t0 = time.perf_counter()
         sig = R.sigma_restricted(g, c, h1, h2)
         times.append(time.perf_counter() - t0)
+    cpu_end = resource.getrusage(resource.RUSAGE_SELF)
+    # cores actually kept busy by the timed builds: process CPU time / wall time
+    busy = ((cpu_end.ru_utime + cpu_end.ru_stime) - (cpu_begin.ru_utime + cpu_begin.ru_stime)) \
+        / max(sum(times), 1e-9)
     mean_s = sum(times) / len(times)
     value = 1.0 / mean_s
     verify = verify_against_golden(sig, args.norb, args.kind, numpy_state=True)
@@ -239,7 +249,8 @@ def run_reference(args):
         "config": config_dict(args.norb, args.kind, args.shard, args.gpus),
         "cpu_baseline": {"value": value, "unit": "sigma/s", "cores": cores,
                          "omp_threads": threads, "kind": "reference", "sample": sample,
-                         "extrapolated": False, "step_seconds": times},
+                         "extrapolated": False, "step_seconds": times,
+                         "busy_cores": busy},
         "sampled_estimate": {"value": 1.0 / est_s, "unit": "sigma/s", "extrapolated": True,
                              "sample": est_desc},
         "verify_rel_err": verify,
@@ -248,6 +259,9 @@ def run_reference(args):
     }
     if threads is not None and threads != cores:
         line["cpu_baseline"]["warning"] = "OpenMP threads != usable cores"
+    if cores > 1 and busy < 1.5:
+        line["cpu_baseline"]["warning"] = ("the reference ran on ~%.1f cores although %d are "
+                                           "usable: this line under-states it" % (busy, cores))
     emit(line)
 
 

@@ -65,56 +65,67 @@ constexpr uint32_t OZ_NONE = 0xFFFFFFFFu;                     // source table en
 // (sum ^ 0x80) is the two's-complement sum of the two signed digits.
 
 __global__ void k_absmax_sumsq(int64_t n2, const double *__restrict__ x, double *__restrict__ part) {
-  // part[2*block] = max |x|, part[2*block+1] = sum x^2 over this block's grid-stride share
-  double mx = 0.0, ss = 0.0;
+  // part[3*block] = max |x|, [3*block+1] = sum x^2, [3*block+2] = number of non-zero x over this
+  // block's grid-stride share
+  double mx = 0.0, ss = 0.0, nz = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2;
        i += (int64_t)gridDim.x * blockDim.x) {
     const double v = x[i];
     mx = fmax(mx, fabs(v));
     ss += v * v;
+    nz += v != 0.0 ? 1.0 : 0.0;
   }
-  __shared__ double s_mx[32], s_ss[32];
+  __shared__ double s_mx[32], s_ss[32], s_nz[32];
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     s_mx[warp] = mx;
     s_ss[warp] = ss;
+    s_nz[warp] = nz;
   }
   __syncthreads();
   if (warp == 0) {
     const int nw = blockDim.x >> 5;
     mx = lane < nw ? s_mx[lane] : 0.0;
     ss = lane < nw ? s_ss[lane] : 0.0;
+    nz = lane < nw ? s_nz[lane] : 0.0;
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      nz += __shfl_xor_sync(0xffffffffu, nz, o);
     }
     if (lane == 0) {
-      part[2 * blockIdx.x] = mx;
-      part[2 * blockIdx.x + 1] = ss;
+      part[3 * blockIdx.x] = mx;
+      part[3 * blockIdx.x + 1] = ss;
+      part[3 * blockIdx.x + 2] = nz;
     }
   }
 }
 
 __global__ void k_absmax_sumsq_final(int nblocks, const double *__restrict__ part,
                                      double *__restrict__ out) {
-  // deterministic second pass: out[0] = max, out[1] = sum of squares, out[2] = scale S
-  double mx = 0.0, ss = 0.0;
+  // deterministic second pass: out[0] = max, out[1] = sum of squares, out[2] = scale S,
+  // out[3] = number of non-zero real / imaginary parts
+  double mx = 0.0, ss = 0.0, nz = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += 32) {
-    mx = fmax(mx, part[2 * i]);
-    ss += part[2 * i + 1];
+    mx = fmax(mx, part[3 * i]);
+    ss += part[3 * i + 1];
+    nz += part[3 * i + 2];
   }
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
   }
   if (threadIdx.x == 0) {
     out[0] = mx;
     out[1] = ss;
     out[2] = 2.0001 * mx;   // |x| / S < 0.5: inside the range of OZ_NS balanced digits
+    out[3] = nz;
   }
 }
 
@@ -887,7 +898,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-constexpr int OZ_STATS_DOUBLES = 4 + 2 * 1024;
+constexpr int OZ_STATS_DOUBLES = 4 + 3 * 1024;
 // workspace bytes of the sliced path: digit planes + statistics block
 static size_t oz_planes_bytes(const fqeb_graph *g) {
   // [layout: by row, transposed][sign][det][part] digit words
@@ -902,21 +913,23 @@ double *ozaki_stats_ptr(const fqeb_graph *g, void *d_oz) {
   return (double *)((char *)d_oz + oz_planes_bytes(g));
 }
 
-// d_stats: device buffer of OZ_STATS_DOUBLES doubles.  Returns max |Re/Im C| and ||C||^2 on the
-// host (one small synchronising copy: the caller decides between this path and the DMMA path).
+// d_stats: device buffer of OZ_STATS_DOUBLES doubles.  Returns max |Re/Im C|, ||C||^2 and the
+// number of non-zero real / imaginary parts on the host (one small synchronising copy: the
+// caller decides between this path and the DMMA path).
 int ozaki_stats(const fqeb_graph *g, const double *d_coeff, double *d_stats, double *h_absmax,
-                double *h_sumsq, cudaStream_t st) {
+                double *h_sumsq, double *h_nonzero, cudaStream_t st) {
   const int64_t ndet = g->len[0] * g->len[1];
   const int nblocks = 1024;
   k_absmax_sumsq<<<nblocks, 256, 0, st>>>(2 * ndet, d_coeff, d_stats + 4);
   FQEB_CHECK_LAUNCH();
   k_absmax_sumsq_final<<<1, 32, 0, st>>>(nblocks, d_stats + 4, d_stats);
   FQEB_CHECK_LAUNCH();
-  double h[2];
+  double h[4];
   FQEB_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
   FQEB_CUDA(cudaStreamSynchronize(st));
   *h_absmax = h[0];
   *h_sumsq = h[1];
+  *h_nonzero = h[3];
   return FQEB_OK;
 }
 
@@ -934,13 +947,16 @@ int ozaki_slice(const fqeb_graph *g, const double *d_coeff, const double *d_stat
   return FQEB_OK;
 }
 
-// estimated relative error of sigma from the global-scale quantisation of C
-double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq) {
+// Estimated relative error of sigma from the global-scale quantisation of C: every NON-ZERO real
+// or imaginary part carries a rounding error of rms u / sqrt(12), u = S 127^-6 the unit of the
+// last digit (zeros are exact, and a part below u / 2 is replaced by zero, an error smaller than
+// that), against ||C||.  A Hartree-Fock determinant or the first Taylor terms grown from it
+// therefore pass (few non-zeros), a dense state with a handful of dominant coefficients does not.
+double ozaki_error_estimate(double absmax, double sumsq, double nonzero) {
   if (!(sumsq > 0.0)) return 0.0;
-  const double ndet = (double)g->len[0] * (double)g->len[1];
-  double q = 2.0001 * absmax * 0.5 / sqrt(3.0);   // rms rounding error in units of the last digit
+  double q = 2.0001 * absmax * 0.5 / sqrt(3.0);   // u / sqrt(12) with u = S 127^-6
   for (int i = 0; i < OZ_NS; ++i) q /= (double)OZ_RADIX;
-  return q * sqrt(2.0 * ndet) / sqrt(sumsq);
+  return q * sqrt(nonzero) / sqrt(sumsq);
 }
 
 static unsigned long long *g_oz_prof = nullptr;

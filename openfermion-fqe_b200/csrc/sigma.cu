@@ -56,10 +56,10 @@ bool ozaki_shape_ok(const fqeb_op *op);
 size_t ozaki_workspace_bytes(const fqeb_graph *g);
 double *ozaki_stats_ptr(const fqeb_graph *g, void *d_oz);
 int ozaki_stats(const fqeb_graph *g, const double *d_coeff, double *d_stats, double *h_absmax,
-                double *h_sumsq, cudaStream_t st);
+                double *h_sumsq, double *h_nonzero, cudaStream_t st);
 int ozaki_slice(const fqeb_graph *g, const double *d_coeff, const double *d_stats, void *d_planes,
                 cudaStream_t st);
-double ozaki_error_estimate(const fqeb_graph *g, double absmax, double sumsq);
+double ozaki_error_estimate(double absmax, double sumsq, double nonzero);
 int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
                  const double *d_stats, int64_t row0, int64_t nrows, int pitch, double *d_evec,
                  int64_t lde, cudaStream_t st);
@@ -236,12 +236,12 @@ static int sigma_build(const fqeb_graph *g, const fqeb_op *op, const double *d_c
     if (sliced) {
       static const double tol = getenv("FQEB_OZAKI_TOL") ? atof(getenv("FQEB_OZAKI_TOL")) : 5e-12;
       d_stats = ozaki_stats_ptr(g, d_workspace);
-      double absmax = 0.0, sumsq = 0.0;
+      double absmax = 0.0, sumsq = 0.0, nonzero = 0.0;
       PhaseTimer t(0, st);
-      rc = ozaki_stats(g, d_coeff, d_stats, &absmax, &sumsq, st);
+      rc = ozaki_stats(g, d_coeff, d_stats, &absmax, &sumsq, &nonzero, st);
       if (rc != FQEB_OK) return rc;
       if (!(sumsq > 0.0)) return FQEB_OK;   // zero vector: sigma is already zero
-      sliced = ozaki_error_estimate(g, absmax, sumsq) <= tol;
+      sliced = ozaki_error_estimate(absmax, sumsq, nonzero) <= tol;
       if (sliced) {
         rc = ozaki_slice(g, d_coeff, d_stats, d_workspace, st);
         if (rc != FQEB_OK) return rc;

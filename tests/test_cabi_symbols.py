@@ -55,10 +55,7 @@ def test_fails_loudly_without_gpu():
         fqe_b200.get_wavefunction(2, 0, 2)
 
 
-def test_plain_c_client_links_and_reports_missing_device(tmp_path):
-    """examples/c_client.c: the boundary is usable from plain C (no Python / torch / C++ in
-    the signatures).  It must compile against include/fqe_b200.h, link to the library and - in
-    a container without a GPU - get FQEB_ERR_NODEVICE instead of a CPU fallback."""
+def _run_c_client(tmp_path):
     import shutil
     import subprocess
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
@@ -73,8 +70,20 @@ def test_plain_c_client_links_and_reports_missing_device(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr
     assert "libfqe_b200 version" in res.stdout
-    import torch
-    if torch.cuda.is_available():
-        assert "|sigma| =" in res.stdout
-    else:
-        assert "no device" in res.stdout and "no CPU fallback" in res.stdout
+    return res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_plain_c_client_links_and_reports_missing_device(tmp_path):
+    """examples/c_client.c: the boundary is usable from plain C (no Python / torch / C++ in
+    the signatures).  It must compile against include/fqe_b200.h, link to the library and - in
+    a container without a GPU - get FQEB_ERR_NODEVICE instead of a CPU fallback."""
+    out = _run_c_client(tmp_path)
+    assert "no device" in out and "no CPU fallback" in out
+
+
+@pytest.mark.gpu
+def test_plain_c_client_builds_sigma_on_the_gpu(tmp_path):
+    """the same client on a GPU box: graph, operator and sigma through the C ABI alone"""
+    out = _run_c_client(tmp_path)
+    assert "|sigma| =" in out and "no device" not in out

@@ -186,6 +186,38 @@ def test_symmetry_switch(monkeypatch, contraction):
     assert O.rel_err(d.apply_operator(op_t).cpu().numpy(), -0.1j * ref) < TOL
 
 
+def test_contraction_path_follows_the_state(monkeypatch):
+    """The INT8-sliced contraction quantises C with ONE global scale; the library estimates the
+    error from max |C|, ||C|| and the number of non-zero parts and falls back to the FP64 DMMA
+    kernel when it is above FQEB_OZAKI_TOL.  A single determinant and a dense random state take
+    the tensor-core path, a dense state with one dominant coefficient the FP64 one; all agree
+    with the oracle."""
+    from fqe_b200 import lib as L, synth
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    monkeypatch.delenv("FQEB_OZAKI", raising=False)
+    monkeypatch.delenv("FQEB_FUSION", raising=False)
+    lib = L.load()
+    na, nb, norb = 4, 4, 8
+    h1, h2 = synth.integrals(norb, "real8")
+    op = DenseOperator(norb, h1, h2)
+    g = O.graph(na, nb, norb)
+    d = FqeData(na, nb, norb)
+    rng = np.random.default_rng(77)
+    dense = _rand_c(rng, (d.lena(), d.lenb()))
+    hf = np.zeros_like(dense)
+    hf[0, 0] = 1.0
+    peaked = 1e-7 * dense
+    peaked[3, 5] = 1.0
+    for state, want, tol in [(dense, 3, 2e-11), (hf, 3, 2e-11), (peaked, 2, 1e-12)]:
+        d.set_wfn(strategy="from_data", raw_data=state)
+        out = d.apply_operator(op).cpu().numpy()
+        assert lib.fqeb_sigma_last_path() == want
+        assert O.rel_err(out, O.sigma_restricted(g, state, h1, h2)) < tol
+    # a zero vector: sigma is zero on either path
+    d.set_wfn(strategy="from_data", raw_data=np.zeros_like(dense))
+    assert not d.apply_operator(op).any()
+
+
 DC_CFGS = [(2, 3, 6), (2, 1, 4), (4, 4, 8), (0, 2, 4), (3, 3, 3), (5, 4, 9)]
 
 
