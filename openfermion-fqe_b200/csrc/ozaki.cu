@@ -130,22 +130,20 @@ __global__ void k_absmax_sumsq_final(int nblocks, const double *__restrict__ par
 }
 
 __device__ __forceinline__ uint64_t balanced_digits(double x, double scale_pow) {
-  // biased digit bytes (most significant slice in byte 0) of x, |x| < 0.5
-  long long n = __double2ll_rn(x * scale_pow);
+  // biased digit bytes (most significant slice in byte 0) of x, |x| < 0.5.
+  // n = rint(x 127^6) is an integer below 2^42, so everything stays exact in FP64: the nearest
+  // integer to n / 127 is q (no ties: 127 is odd; the product n * (1/127) is off by far less than
+  // the 1/254 that separates n / 127 from a half-integer) and d = n - 127 q is the balanced digit
+  // in [-63, 63] - the same digits as 64-bit integer division gives, at a tenth of the
+  // instructions (the integer version made this kernel ALU-bound: 3.7 ms for 13 GB).
+  double n = rint(x * scale_pow);
   uint64_t w = 0x4040000000000000ull;   // bytes 6, 7: digit 0
 #pragma unroll
   for (int s = OZ_NS - 1; s >= 0; --s) {
-    long long q = n / OZ_RADIX;
-    long long d = n - q * OZ_RADIX;               // truncated remainder in (-127, 127)
-    if (d > 63) {
-      d -= OZ_RADIX;
-      q += 1;
-    } else if (d < -63) {
-      d += OZ_RADIX;
-      q -= 1;
-    }
+    const double q = rint(n * (1.0 / (double)OZ_RADIX));
+    const int d = __double2int_rn(fma(-(double)OZ_RADIX, q, n));
     n = q;
-    w |= (uint64_t)(d + 64) << (8 * s);
+    w |= (uint64_t)(uint32_t)(d + 64) << (8 * s);
   }
   return w;
 }
