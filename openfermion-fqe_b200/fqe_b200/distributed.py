@@ -186,6 +186,24 @@ def sharded_apply_host(sector, op, host_coeff: torch.Tensor, host_sigma: torch.T
     if r1 > r0:
         buffers.cstore[r0:r1].copy_(host_coeff[r0:r1], non_blocking=True)
     buffers.gather_coeff()
+    nslices = int(settings.allreduce_slices)
+    if world == 1 and nslices > 1:
+        # one GPU: the scatter of the last chunk is issued by slices of target rows and every
+        # finished slice starts its way home on a side stream while the next one is scattered
+        lena = sector.lena()
+        sig, pending = buffers.data.apply_operator(op, out=buffers.sstore[:lena],
+                                                   defer_last_scatter=True)
+        main, side = torch.cuda.current_stream(), _side_stream(sig.device)
+        for x0, x1 in split_even(lena, nslices):
+            if x1 == x0:
+                continue
+            buffers.data.finish_scatter(pending, x0, x1, sig)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                host_sigma[x0:x1].copy_(sig[x0:x1], non_blocking=True)
+        main.wait_stream(side)
+        main.synchronize()
+        return
     mine = buffers.build(op, mode)
     if r1 > r0:
         host_sigma[r0:r1].copy_(mine, non_blocking=True)

@@ -413,3 +413,23 @@ def test_deferred_scatter_by_target_slices(kind):
     sig, pend = d.apply_operator(op, defer_last_scatter=True)
     assert lib.fqeb_scatter_rows(d._core.handle, ctypes.byref(pend), 5, 3, sig.data_ptr(), None) \
         == L.ERR_INVALID
+
+
+def test_host_buffer_apply_single_gpu():
+    """sharded_apply_host on one GPU (pinned host buffers in, pinned host buffers out, the
+    download overlapped with the sliced scatter of the last chunk) equals the resident build"""
+    from fqe_b200.distributed import ExchangeBuffers, sharded_apply_host
+    from fqe_b200.fqe_data import DenseOperator, FqeData
+    na, nb, norb = 4, 4, 8
+    g, c, h1, h2 = _case(na, nb, norb, "real8")
+    d = FqeData(na, nb, norb)
+    d.set_wfn(strategy="from_data", raw_data=c)
+    op = DenseOperator(norb, h1, h2)
+    ref = d.apply_operator(op).cpu()
+    host_c = torch.from_numpy(np.ascontiguousarray(c)).pin_memory()
+    host_s = torch.empty_like(host_c).pin_memory()
+    bufs = ExchangeBuffers(d, 1, 0)
+    for _ in range(2):   # buffers are reusable
+        host_s.zero_()
+        sharded_apply_host(d, op, host_c, host_s, "det", bufs)
+        assert torch.equal(host_s, ref)
