@@ -47,11 +47,14 @@ __device__ __forceinline__ void gr_dmma(double &c0, double &c1, double a, double
 __global__ void __launch_bounds__(GR_THREADS, 2)
 k_gram(int M, int N, int64_t ncols, int64_t slab, const double2 *__restrict__ bra, int64_t ldb,
        const double2 *__restrict__ ket, int64_t ldk, const double2 *__restrict__ ket_extra,
-       double2 *__restrict__ part) {
+       double2 *__restrict__ part, int upper_only) {
   extern __shared__ __align__(16) double gr_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_n = (N + GR_TN - 1) / GR_TN;
   const int m0 = (blockIdx.x / tiles_n) * GR_TM, n0 = (blockIdx.x % tiles_n) * GR_TN;
+  // bra == ket: G is Hermitian; blocks strictly below the diagonal are left to the caller's
+  // mirror (their partial sums stay zero: the scratch buffer is cleared first)
+  if (upper_only && n0 + GR_TN <= m0) return;
   const int64_t c_begin = (int64_t)blockIdx.y * slab;
   const int64_t c_end = c_begin + slab < ncols ? c_begin + slab : ncols;
   const int nstage = c_end > c_begin ? (int)((c_end - c_begin + GR_KS - 1) / GR_KS) : 0;
@@ -95,7 +98,7 @@ k_gram(int M, int N, int64_t ncols, int64_t slab, const double2 *__restrict__ br
     const double *pa = sa + (16 * wm + fr) * GR_LD + fk;
     const double *pb = sb + (32 * wn + fr) * GR_LD + fk;
     const double *pb_x = sb + (32 * wn + fr) * GR_LD + (fk ^ 1);
-    const double sgn = (fk & 1) ? -1.0 : 1.0;
+    const unsigned long long flip = (fk & 1) ? 0x8000000000000000ull : 0ull;   // sign of ket'
 #pragma unroll
     for (int k4 = 0; k4 < 2 * GR_KS / 4; ++k4) {
       double a[2], b[4], bx[4];
@@ -104,7 +107,7 @@ k_gram(int M, int N, int64_t ncols, int64_t slab, const double2 *__restrict__ br
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         b[j] = pb[j * 8 * GR_LD + 4 * k4];
-        bx[j] = sgn * pb_x[j * 8 * GR_LD + 4 * k4];
+        bx[j] = __longlong_as_double(__double_as_longlong(pb_x[j * 8 * GR_LD + 4 * k4]) ^ flip);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -133,15 +136,27 @@ k_gram(int M, int N, int64_t ncols, int64_t slab, const double2 *__restrict__ br
   }
 }
 
-__global__ void k_gram_reduce(int64_t n, int nslab, const double2 *__restrict__ part,
-                              double2 *__restrict__ out) {
+// out[m][n] += sum over slabs of part[slab][m][n] in slab order (bitwise reproducible).  With
+// herm_tile > 0 the blocks strictly below the block diagonal were not computed: those elements
+// take the conjugate of the mirrored partial sums instead.
+__global__ void k_gram_reduce(int64_t n, int nslab, int M, int N, int herm_tile,
+                              const double2 *__restrict__ part, double2 *__restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  int64_t src = i;
+  double conj = 1.0;
+  if (herm_tile > 0) {
+    const int m = (int)(i / N), c = (int)(i % N);
+    if ((c / herm_tile + 1) * herm_tile <= (m / herm_tile) * herm_tile) {   // block not computed
+      src = (int64_t)c * N + m;   // c < m < M: a valid row
+      conj = -1.0;
+    }
+  }
   double2 acc = out[i];
-  for (int s = 0; s < nslab; ++s) {   // fixed order: bitwise reproducible
-    const double2 v = part[(size_t)s * n + i];
+  for (int s = 0; s < nslab; ++s) {   // fixed order
+    const double2 v = part[(size_t)s * n + src];
     acc.x += v.x;
-    acc.y += v.y;
+    acc.y += conj * v.y;
   }
   out[i] = acc;
 }
@@ -164,9 +179,22 @@ extern "C" int fqeb_gram_accumulate(int M, int N, int64_t ncols, const double *d
   FQEB_REQUIRE(ldb >= ncols && (N == 1 && d_ket_last ? true : ldk >= ncols),
                "gram: leading dimension smaller than the column count");
   cudaStream_t st = (cudaStream_t)stream;
-  const int tiles = ((M + GR_TM - 1) / GR_TM) * ((N + GR_TN - 1) / GR_TN);
-  // enough slabs for two CTAs on every SM, whole stages per slab
-  int64_t nslab = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  const int tiles_m = (M + GR_TM - 1) / GR_TM, tiles_n = (N + GR_TN - 1) / GR_TN;
+  const int tiles = tiles_m * tiles_n;
+  // Hermitian case (bra and ket are the same rows): only the blocks on and above the diagonal
+  // are computed; k_gram_reduce fills G[n][m] = conj(G[m][n]) for the rest
+  const bool herm = d_bra == d_ket && ldb == ldk && (d_ket_last ? N == M + 1 : N == M);
+  int active = tiles;
+  if (herm) {
+    active = 0;
+    for (int tm = 0; tm < tiles_m; ++tm)
+      for (int tn = 0; tn < tiles_n; ++tn)
+        if (!((tn + 1) * GR_TN <= tm * GR_TM)) ++active;
+  }
+  // ONE wave: as many column slabs as fit two CTAs per SM with the blocks that do work
+  // (one CTA more than fits costs a whole second wave), whole stages per slab
+  int64_t nslab = (2 * (int64_t)sm_count()) / active;
+  if (nslab < 1) nslab = 1;
   const int64_t stages = (ncols + GR_KS - 1) / GR_KS;
   if (nslab > stages) nslab = stages;
   if (nslab > 65535) nslab = 65535;
@@ -174,18 +202,23 @@ extern "C" int fqeb_gram_accumulate(int M, int N, int64_t ncols, const double *d
   nslab = (ncols + slab - 1) / slab;
   double2 *part = nullptr;
   FQEB_CUDA(cudaMallocAsync((void **)&part, sizeof(double2) * (size_t)nslab * M * N, st));
+  if (herm) FQEB_CUDA(cudaMemsetAsync(part, 0, sizeof(double2) * (size_t)nslab * M * N, st));
   const size_t smem = sizeof(double) * (size_t)GR_STAGES * 2 * GR_PANEL;
   static bool attr_set = false;
   if (!attr_set) {
     FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs of 108 KB per SM: ask for the largest shared-memory carve-out
+    FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   k_gram<<<dim3((unsigned)tiles, (unsigned)nslab), GR_THREADS, smem, st>>>(
       M, N, ncols, slab, (const double2 *)d_bra, ldb, (const double2 *)d_ket, ldk,
-      (const double2 *)d_ket_last, part);
+      (const double2 *)d_ket_last, part, herm ? 1 : 0);
   FQEB_CHECK_LAUNCH();
   const int64_t n = (int64_t)M * N;
-  k_gram_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, (int)nslab, part, (double2 *)d_G);
+  k_gram_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, (int)nslab, M, N,
+                                                             herm ? GR_TM : 0, part,
+                                                             (double2 *)d_G);
   FQEB_CHECK_LAUNCH();
   FQEB_CUDA(cudaFreeAsync(part, st));
   return FQEB_OK;

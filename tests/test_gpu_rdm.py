@@ -132,6 +132,19 @@ def test_gram_kernel_against_torch():
         ref = g0 + bra[:, :ncols].conj() @ full.transpose(0, 1)
         err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
         assert err < 1e-13, (m, n, ncols, err)
+        if nk == m:
+            # bra and ket the same buffer: the Hermitian shortcut (blocks below the diagonal are
+            # mirrored instead of computed) must give the same matrix
+            h = g0.clone()
+            L.call("fqeb_gram_accumulate", m, n, ncols, bra.data_ptr(), ld, bra.data_ptr(), ld,
+                   last.data_ptr() if extra else None, h.data_ptr(),
+                   torch.cuda.current_stream().cuda_stream)
+            fullh = bra[:, :ncols]
+            if extra:
+                fullh = torch.cat([fullh, last[None, :]], dim=0)
+            refh = g0 + bra[:, :ncols].conj() @ fullh.transpose(0, 1)
+            errh = (h - refh).abs().max().item() / max(1.0, refh.abs().max().item())
+            assert errh < 1e-13, (m, n, ncols, errh)
         # bitwise reproducible
         again = g0.clone()
         L.call("fqeb_gram_accumulate", m, n, ncols, bra.data_ptr(), ld,
