@@ -95,6 +95,9 @@ struct PhaseTimer {
 };
 
 static std::atomic<int> g_last_path{0};   // FQEB_PATH_* of the most recent two-body sigma build
+// Factor on FQEB_OZAKI_TOL for the builds issued by this thread: fqeb_taylor loosens the
+// quantisation bound for terms whose weight in the propagated state is small (see there).
+static thread_local double g_ozaki_tol_scale = 1.0;
 
 struct ChunkLayout {
   bool fused;         // D never materialised (k_sigma_fused / k_sigma_ozaki)
@@ -241,7 +244,7 @@ static int sigma_build(const fqeb_graph *g, const fqeb_op *op, const double *d_c
       rc = ozaki_stats(g, d_coeff, d_stats, &absmax, &sumsq, &nonzero, st);
       if (rc != FQEB_OK) return rc;
       if (!(sumsq > 0.0)) return FQEB_OK;   // zero vector: sigma is already zero
-      sliced = ozaki_error_estimate(absmax, sumsq, nonzero) <= tol;
+      sliced = ozaki_error_estimate(absmax, sumsq, nonzero) <= tol * g_ozaki_tol_scale;
       if (sliced) {
         rc = ozaki_slice(g, d_coeff, d_stats, d_workspace, st);
         if (rc != FQEB_OK) return rc;
@@ -368,6 +371,20 @@ extern "C" int fqeb_taylor(const fqeb_graph *g, const fqeb_op *op, double *d_evo
   cudaStream_t st = (cudaStream_t)stream;
   FQEB_CUDA(cudaMemcpyAsync(d_work, d_evol, sizeof(double) * 2 * (size_t)n,
                             cudaMemcpyDeviceToDevice, st));
+  // Error budget of the sliced contraction inside the series: a relative error delta_k of the
+  // sigma build that produces term k enters the propagated state with the weight of that term
+  // (and of the later ones grown from it), ~ delta_k ||term_k||.  Holding every build to the
+  // same relative bound would send the late, tiny terms - whose vectors grow heavy tails and
+  // fail the global-scale estimate - to the slower FP64 kernel for no gain in the result, so the
+  // bound is scaled by ||C|| / (4 ||term_{k-1}||), at least 1, at most 1e4: the absolute error
+  // added per term stays below a quarter of what the first term may add.
+  struct TolScaleGuard {
+    ~TolScaleGuard() { g_ozaki_tol_scale = 1.0; }
+  } tol_guard;
+  double norm0_sq = 0.0;
+  rc = fqeb_znorm2(n, d_evol, d_scratch, &norm0_sq, stream);
+  if (rc != FQEB_OK) return rc;
+  const double norm0 = sqrt(norm0_sq);
   double factorial = 1.0;
   for (int order = 1; order < max_terms; ++order) {
     rc = fqeb_sigma_restricted(g, op, d_work, d_next, d_workspace, workspace_bytes, 0, g->len[0],
@@ -381,10 +398,13 @@ extern "C" int fqeb_taylor(const fqeb_graph *g, const fqeb_op *op, double *d_evo
     double norm2 = 0.0;
     rc = fqeb_axpy_norm2(n, coeff, 0.0, d_work, d_evol, d_scratch, &norm2, stream);
     if (rc != FQEB_OK) return rc;
-    if (sqrt(norm2) * coeff < accuracy) {
+    const double term_norm = sqrt(norm2) * coeff;
+    if (term_norm < accuracy) {
       *nterms = order;
       return FQEB_OK;
     }
+    double scale = term_norm > 0.0 ? 0.25 * norm0 / term_norm : 1.0;
+    g_ozaki_tol_scale = scale < 1.0 ? 1.0 : (scale > 1.0e4 ? 1.0e4 : scale);
   }
   *nterms = max_terms;
   set_error("maximum taylor expansion limit reached (%d terms)", max_terms);
