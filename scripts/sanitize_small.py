@@ -36,6 +36,17 @@ for (n, sz, norb) in [(4, 0, 4), (5, 1, 6), (6, 0, 7), (8, 0, 8)]:
     sec.apply_individual_nbody(0.3, [norb - 1], [0], [1], [2])
     sec.evolve_individual_nbody_nontrivial(0.2, 0.4 + 0.1j, [norb - 1], [0], [1], [2])
     sec.rdm12()
+    sec.rdm12(w2.sector((n, sz)))                      # transition form of the Gram kernel
+    wfn.rdm("i j^ k^ l")
+    from fqe_b200.fqe_data import DenseOperator
+    opd = DenseOperator(norb, h1, 0.1 * h2)
+    for ozaki in ("1", "0"):                           # sliced and FP64 contraction, deferred scatter
+        os.environ["FQEB_OZAKI"] = ozaki
+        sig, pend = sec.apply_operator(opd, defer_last_scatter=True)
+        half = sec.lena() // 2
+        sec.finish_scatter(pend, 0, half, sig)
+        sec.finish_scatter(pend, half, sec.lena(), sig)
+    os.environ.pop("FQEB_OZAKI")
     wfn.norm(); wfn.vdot(wfn); wfn.scale(0.5); wfn.ax_plus_y(0.1, w2)
     if norb <= 6:
         h3 = 0.01 * np.ones((norb,) * 6, dtype=complex)
