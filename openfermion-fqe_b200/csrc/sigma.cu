@@ -23,6 +23,7 @@
 // sigma that one allreduce completes.
 #include "fqeb_common.cuh"
 
+#include <math.h>
 #include <string.h>
 #include <map>
 #include <condition_variable>
@@ -243,8 +244,10 @@ static int sigma_build(const fqeb_graph *g, const fqeb_op *op, const double *d_c
       PhaseTimer t(0, st);
       rc = ozaki_stats(g, d_coeff, d_stats, &absmax, &sumsq, &nonzero, st);
       if (rc != FQEB_OK) return rc;
-      if (!(sumsq > 0.0)) return FQEB_OK;   // zero vector: sigma is already zero
-      sliced = ozaki_error_estimate(absmax, sumsq, nonzero) <= tol * g_ozaki_tol_scale;
+      if (sumsq == 0.0) return FQEB_OK;   // zero vector: sigma is already zero
+      // NaN / Inf in the state: no fixed-point image exists; the FP64 kernel propagates them
+      sliced = isfinite(sumsq) && isfinite(absmax) &&
+               ozaki_error_estimate(absmax, sumsq, nonzero) <= tol * g_ozaki_tol_scale;
       if (sliced) {
         rc = ozaki_slice(g, d_coeff, d_stats, d_workspace, st);
         if (rc != FQEB_OK) return rc;

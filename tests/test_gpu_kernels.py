@@ -216,6 +216,12 @@ def test_contraction_path_follows_the_state(monkeypatch):
     # a zero vector: sigma is zero on either path
     d.set_wfn(strategy="from_data", raw_data=np.zeros_like(dense))
     assert not d.apply_operator(op).any()
+    # NaN in the state is propagated (FP64 path), not silently replaced by zeros
+    bad = dense.copy()
+    bad[2, 2] = np.nan
+    d.set_wfn(strategy="from_data", raw_data=bad)
+    out = d.apply_operator(op)
+    assert lib.fqeb_sigma_last_path() == 2 and bool(torch.isnan(torch.view_as_real(out)).any())
 
 
 DC_CFGS = [(2, 3, 6), (2, 1, 4), (4, 4, 8), (0, 2, 4), (3, 3, 3), (5, 4, 9)]
