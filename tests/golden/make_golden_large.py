@@ -243,6 +243,31 @@ def main():
             del out, wfn
             save()
 
+    # ---- 1- and 2-particle RDMs (plain and transition) at norb = 10 and 12 ------------------
+    if only in (None, "rdm"):
+        for norb in (10, 12):
+            n, sz = norb, 0
+            na, nb, la, lb = synth.sector_dims(n, sz, norb)
+            ket = synth.state(la, lb, seed=synth.seed_for(norb, 54))
+            bra = synth.state(la, lb, seed=synth.seed_for(norb, 55))
+            ksec = wavefunction(n, sz, norb, ket).sector((n, sz))
+            bsec = wavefunction(n, sz, norb, bra).sector((n, sz))
+            t0 = time.perf_counter()
+            r1, r2 = ksec.rdm12()
+            t1, t2 = ksec.rdm12(bsec)
+            dt = time.perf_counter() - t0
+            rng = np.random.default_rng(20262400 + norb)
+            pick = rng.choice(norb ** 4, size=4096, replace=False)
+            for tag, a1, a2 in ((f"rdm{norb}", r1, r2), (f"trdm{norb}", t1, t2)):
+                store[f"{tag}_1"] = np.asarray(a1)
+                store[f"{tag}_2_idx"] = pick
+                store[f"{tag}_2_val"] = np.asarray(a2).reshape(-1)[pick]
+                store[f"{tag}_2_norm"] = np.array([np.linalg.norm(a2)])
+                store[f"{tag}_2_trace"] = np.array([np.einsum("ijij", a2)])
+            store[f"rdm{norb}_meta"] = np.array([n, sz, norb])
+            print(f"rdm12 norb={norb}: trace(rdm1) {np.trace(r1):.12f}  {dt:.1f} s", flush=True)
+            save()
+
 
 if __name__ == "__main__":
     main()

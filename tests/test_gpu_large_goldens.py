@@ -168,3 +168,33 @@ def test_dense_three_body_profile_shape(large, norb):
     _check(large, tag, out.get_coeff_device((n, sz)))
     del out, wfn
     release_workspace()
+
+
+@pytest.mark.parametrize("norb", [10, 12])
+def test_rdm12_at_scale(large, norb):
+    """FqeData.rdm12, plain and transition, against the reference's own output at norb = 10 and
+    12 (reference fqe_data.py:1726-1838): rdm1 in full, rdm2 through its norm, its ijij trace and
+    4096 sampled entries; the reductions run on the library's Gram kernel (Hermitian shortcut for
+    the plain form, general form for the transition one)."""
+    import fqe_b200 as fqe
+    from fqe_b200 import synth
+    if f"rdm{norb}_meta" not in large:
+        pytest.skip(f"rdm{norb} not in ref_large.npz")
+    n, sz = norb, 0
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    ket = fqe.Wavefunction([[n, sz, norb]])
+    ket.set_wfn(strategy="from_data",
+                raw_data={(n, sz): synth.state(la, lb, seed=synth.seed_for(norb, 54))})
+    bra = fqe.Wavefunction([[n, sz, norb]])
+    bra.set_wfn(strategy="from_data",
+                raw_data={(n, sz): synth.state(la, lb, seed=synth.seed_for(norb, 55))})
+    ksec, bsec = ket.sector((n, sz)), bra.sector((n, sz))
+    for tag, (g1, g2) in ((f"rdm{norb}", ksec.rdm12()), (f"trdm{norb}", ksec.rdm12(bsec))):
+        r1 = large[f"{tag}_1"]
+        assert np.abs(g1 - r1).max() < 1e-11 * np.abs(r1).max(), tag
+        flat = g2.reshape(-1)
+        scale = float(large[f"{tag}_2_norm"][0])
+        assert abs(np.linalg.norm(g2) - scale) < 1e-11 * scale, tag
+        assert np.abs(flat[large[f"{tag}_2_idx"]] - large[f"{tag}_2_val"]).max() < \
+            1e-11 * np.abs(large[f"{tag}_2_val"]).max(), tag
+        assert abs(np.einsum("ijij", g2) - large[f"{tag}_2_trace"][0]) < 1e-10 * scale, tag
