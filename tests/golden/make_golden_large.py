@@ -243,6 +243,39 @@ def main():
             del out, wfn
             save()
 
+    # ---- Chebyshev propagator and an orbital rotation (transform) at norb = 12 ---------------
+    if only in (None, "cheb12"):
+        from scipy.linalg import expm
+        norb, n, sz = 12, 12, 0
+        na, nb, la, lb = synth.sector_dims(n, sz, norb)
+        h1, h2 = synth.integrals(norb, "real8", scale=0.05)
+        e0 = 0.25
+        ham = fqe.get_restricted_hamiltonian((h1, h2), e_0=e0)
+        c0 = synth.state(la, lb, seed=synth.seed_for(norb, 56))
+        wfn = wavefunction(n, sz, norb, c0)
+        x = wfn
+        for _ in range(4):
+            y = x.apply(ham)
+            hn = y.norm()
+            y.scale(1.0 / hn)
+            x = y
+        lim = [float(f"{-1.2 * hn:.3g}"), float(f"{1.2 * hn:.3g}")]   # generous spectral bounds
+        t = float(f"{2.0 / hn:.2g}")
+        t0 = time.perf_counter()
+        ch = wfn.apply_generated_unitary(t, "chebyshev", ham, spec_lim=lim).get_coeff((n, sz))
+        dt = time.perf_counter() - t0
+        put(store, "cheb12", signature(ch, 20262512), meta=[n, sz, norb], t=[t], e0=[e0],
+            scale=[0.05], spec_lim=lim, ref_seconds=[dt])
+        print("cheb12 norm", np.linalg.norm(ch), "lim", lim, "t", t, f"{dt:.1f} s", flush=True)
+        rng = np.random.default_rng(20262513)
+        a = rng.standard_normal((norb, norb)) + 1j * rng.standard_normal((norb, norb))
+        rot = expm(-0.3j * (a + a.conj().T))
+        w2 = wavefunction(n, sz, norb, c0)
+        w2.transform(rot)
+        put(store, "transform12", signature(w2.get_coeff((n, sz)), 20262514), rot=rot)
+        print("transform12 norm", w2.norm(), flush=True)
+        save()
+
     # ---- 1- and 2-particle RDMs (plain and transition) at norb = 10 and 12 ------------------
     if only in (None, "rdm"):
         for norb in (10, 12):

@@ -198,3 +198,31 @@ def test_rdm12_at_scale(large, norb):
         assert np.abs(flat[large[f"{tag}_2_idx"]] - large[f"{tag}_2_val"]).max() < \
             1e-11 * np.abs(large[f"{tag}_2_val"]).max(), tag
         assert abs(np.einsum("ijij", g2) - large[f"{tag}_2_trace"][0]) < 1e-10 * scale, tag
+
+
+def test_chebyshev_and_transform_norb12(large):
+    """apply_generated_unitary(algo='chebyshev') (reference wavefunction.py:570-611) and
+    Wavefunction.transform (:813-959) at norb = 12 against the reference's own outputs"""
+    import fqe_b200 as fqe
+    from fqe_b200 import synth
+    from fqe_b200.fqe_data import release_workspace
+    if "cheb12_norm" not in large:
+        pytest.skip("cheb12 not in ref_large.npz")
+    n, sz, norb = [int(x) for x in large["cheb12_meta"]]
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    h1, h2 = synth.integrals(norb, "real8", scale=float(large["cheb12_scale"][0]))
+    ham = fqe.get_restricted_hamiltonian((h1, h2), e_0=float(large["cheb12_e0"][0]))
+    c0 = synth.state(la, lb, seed=synth.seed_for(norb, 56))
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0})
+    t, lim = float(large["cheb12_t"][0]), [float(x) for x in large["cheb12_spec_lim"]]
+    for path in ("default", "dmma_fused"):
+        with _Env(**PATHS[path]):
+            ch = wfn.apply_generated_unitary(t, "chebyshev", ham, spec_lim=lim)
+            _check(large, "cheb12", ch.get_coeff_device((n, sz)))
+            del ch
+    w2 = fqe.Wavefunction([[n, sz, norb]])
+    w2.set_wfn(strategy="from_data", raw_data={(n, sz): c0})
+    w2.transform(large["transform12_rot"])
+    _check(large, "transform12", w2.get_coeff_device((n, sz)))
+    release_workspace()
