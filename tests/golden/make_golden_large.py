@@ -276,6 +276,33 @@ def main():
         print("transform12 norm", w2.norm(), flush=True)
         save()
 
+    # ---- individual n-body operators at norb = 12 (BASELINE config 5, the sweep) -------------
+    if only in (None, "nbody12"):
+        norb, n, sz = 12, 12, 0
+        na, nb, la, lb = synth.sector_dims(n, sz, norb)
+        c0 = synth.state(la, lb, seed=synth.seed_for(norb, 57))
+        sec = wavefunction(n, sz, norb, c0).sector((n, sz))
+        coeff, tm = 0.3 - 0.2j, 0.41
+        ops = [([11, 4, 1], [9, 3, 0], [], []), ([7, 2], [5, 0], [10], [3]),
+               ([6], [1], [8, 3], [11, 2]), ([], [], [9, 5, 0], [10, 4, 2]),
+               ([5, 3], [5, 3], [7], [7])]
+        store["nbody12_ops"] = np.array([repr(o) for o in ops])
+        store["nbody12_coeff"], store["nbody12_time"] = np.array([coeff]), np.array([tm])
+        store["nbody12_meta"] = np.array([n, sz, norb])
+        for k, (da, ua, db, ub) in enumerate(ops):
+            out = sec.apply_individual_nbody(coeff, da, ua, db, ub).coeff
+            put(store, f"nbody12_apply{k}", signature(out, 20262600 + k))
+            if da == ua and db == ub:
+                tmp = wavefunction(n, sz, norb, c0.copy()).sector((n, sz))
+                tmp.evolve_inplace_individual_nbody_trivial(tm, coeff, da, db)
+                ev = tmp.coeff
+            else:
+                ev = sec.evolve_individual_nbody_nontrivial(tm, coeff, da, ua, db, ub).coeff
+            put(store, f"nbody12_evolve{k}", signature(ev, 20262650 + k))
+            print(f"nbody12 op {k}: |apply| {np.linalg.norm(out):.6f} |evolve| {np.linalg.norm(ev):.6f}",
+                  flush=True)
+        save()
+
     # ---- 1- and 2-particle RDMs (plain and transition) at norb = 10 and 12 ------------------
     if only in (None, "rdm"):
         for norb in (10, 12):

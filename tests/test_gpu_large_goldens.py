@@ -226,3 +226,32 @@ def test_chebyshev_and_transform_norb12(large):
     w2.transform(large["transform12_rot"])
     _check(large, "transform12", w2.get_coeff_device((n, sz)))
     release_workspace()
+
+
+def test_individual_nbody_norb12(large):
+    """individual n-body operators at norb = 12 (BASELINE config 5's sweep shape): apply and exact
+    evolution (reference fqe_data.py:1558-1653, 2385-2590) against the reference's own outputs"""
+    import ast
+    import fqe_b200 as fqe
+    from fqe_b200 import synth
+    if "nbody12_meta" not in large:
+        pytest.skip("nbody12 not in ref_large.npz")
+    n, sz, norb = [int(x) for x in large["nbody12_meta"]]
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    c0 = synth.state(la, lb, seed=synth.seed_for(norb, 57))
+    wfn = fqe.Wavefunction([[n, sz, norb]])
+    wfn.set_wfn(strategy="from_data", raw_data={(n, sz): c0})
+    sec = wfn.sector((n, sz))
+    zc, tm = complex(large["nbody12_coeff"][0]), float(large["nbody12_time"][0])
+    for k, o in enumerate(large["nbody12_ops"]):
+        da, ua, db, ub = ast.literal_eval(str(o))
+        out = sec.apply_individual_nbody(zc, da, ua, db, ub)
+        _check(large, f"nbody12_apply{k}", out.coeff)
+        if da == ua and db == ub:
+            tmp = fqe.Wavefunction([[n, sz, norb]])
+            tmp.set_wfn(strategy="from_data", raw_data={(n, sz): c0})
+            tmp.sector((n, sz)).evolve_inplace_individual_nbody_trivial(tm, zc, da, db)
+            _check(large, f"nbody12_evolve{k}", tmp.sector((n, sz)).coeff)
+        else:
+            ev = sec.evolve_individual_nbody_nontrivial(tm, zc, da, ua, db, ub)
+            _check(large, f"nbody12_evolve{k}", ev.coeff)
