@@ -3,13 +3,15 @@
 
 Run in the build container only (needs /root/reference; minutes of CPU per case):
 
-    python tests/golden/make_golden_large.py [--only sigma14|sigma16|taylor14|dc16|body3]
+    python tests/golden/make_golden_large.py [--only sigma14|sigma16|taylor14|dc16|body3|cheb12|nbody12|rdm]
 
 The UNMODIFIED reference (built from source by make_golden.build_reference, imported behind
 the openfermion/cirq stand-ins) is driven through its public API -- FqeData.apply (the C
 ``lm`` path, fqe_data.py:685-710), Wavefunction.time_evolve (wavefunction.py:961-1054, Taylor
 548-568), apply/evolve of a DiagonalCoulomb (lib/fqe_data.c:455-602), the dense 3-body apply
-(fqe_data.py:1166-1216 on profiling/profile_3_body.py's tensor) -- on the seeded inputs of
+(fqe_data.py:1166-1216 on profiling/profile_3_body.py's tensor), the Chebyshev propagator and
+Wavefunction.transform at norb=12, individual 3-body operators at norb=12 and rdm12 (plain and
+transition) at norb=10 and 12 -- on the seeded inputs of
 ``fqe_b200.synth`` (the ones bench.py and the -m gpu tests regenerate from their seeds).
 
 A full state at norb=16 is 2.65 GB, so what is committed per state is a SIGNATURE (kilobytes):

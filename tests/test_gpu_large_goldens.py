@@ -9,6 +9,7 @@ container (tests/golden/make_golden_large.py):
   Taylor time_evolve at (7,7,14)                   wavefunction.py:548-568, 961-1054
   DiagonalCoulomb apply / evolve at (8,8,16), non-symmetric v     lib/fqe_data.c:455-602
   dense 3-body apply at norb=10, profile_3_body.py's tensor       fqe_data.py:1166-1216
+  Chebyshev propagator, transform, individual 3-body operators at norb=12; rdm12 at norb=10, 12
 
 Every sigma case runs on the default path AND on each alternative contraction path
 (FQEB_FUSION=0: gather -> DMMA GEMM -> scatter;  FQEB_OZAKI=0: FP64 DMMA instead of the
