@@ -520,10 +520,21 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
   const uint32_t bar_full = oz_smem_u32(&s_bar[0]), bar_free = oz_smem_u32(&s_bar[1]);
   const uint32_t bar_sfull = oz_smem_u32(&s_bar[2]), bar_sfree = oz_smem_u32(&s_bar[2 + OZ2_NSLOT]);
 
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
-    uint4 *dst = reinterpret_cast<uint4 *>(s_b);
-    for (int i = tid; i < p.img_bytes / 16; i += OZ2_THREADS) dst[i] = src[i];
+  // the operand image (117 KB) comes into shared memory as ONE bulk copy of the TMA unit,
+  // completing on an mbarrier (s_bar_img) while the other barriers and TMEM are set up
+  __shared__ __align__(8) uint64_t s_bar_img;
+  const uint32_t bar_img = oz_smem_u32(&s_bar_img);
+  if (tid == 0) {
+    oz_mbar_init(bar_img, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img),
+                 "r"((uint32_t)p.img_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            oz_smem_u32(s_b)),
+        "l"(p.img), "r"((uint32_t)p.img_bytes), "r"(bar_img)
+        : "memory");
   }
   if (tid == 0) {
     oz_mbar_init(bar_full, OZ2_PRODUCERS);
@@ -542,6 +553,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) k_sigma_ozaki2(const OzParams 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  oz_mbar_wait(bar_img, 0);   // operand image has landed (written by the async proxy)
   const uint32_t tmem = s_tmem;
   const int64_t my_tiles =
       (int64_t)blockIdx.x < p.ntiles ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
