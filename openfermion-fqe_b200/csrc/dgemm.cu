@@ -642,13 +642,14 @@ static int launch_ws(const fqeb_op *op, const double *d_A, int a_col0, const dou
   const bool ragged = (m_valid % BM) != 0;
   auto kern = ragged ? k_dgemm_ws<CPLX, WARPS_M, WM, WN, true, KS, NST>
                      : k_dgemm_ws<CPLX, WARPS_M, WM, WN, false, KS, NST>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSize attr_dev;
+  int attr_dev_id = 0;
+  if (attr_dev.needs(1, &attr_dev_id)) {
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, true, KS, NST>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm_ws<CPLX, WARPS_M, WM, WN, false, KS, NST>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
+    attr_dev.record(attr_dev_id, 1);
   }
   const int nmb = (m_valid + BM - 1) / BM;
   const int64_t tiles = nnb * nmb;
@@ -686,13 +687,14 @@ static int launch_shape(const fqeb_op *op, const double *d_A, int a_col0, const 
   constexpr size_t SMEM = sizeof(double) * (size_t)(BM * A_STRIDE + B_TILE) * STAGES;
   const bool ragged = (m_valid % BM) != 0;
   auto kern = ragged ? k_dgemm<CPLX, WARPS_M, WM, WN, true> : k_dgemm<CPLX, WARPS_M, WM, WN, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSize attr_dev;
+  int attr_dev_id = 0;
+  if (attr_dev.needs(1, &attr_dev_id)) {
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     FQEB_CUDA(cudaFuncSetAttribute(k_dgemm<CPLX, WARPS_M, WM, WN, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
+    attr_dev.record(attr_dev_id, 1);
   }
   const int nmb = (m_valid + BM - 1) / BM;
   const int64_t tiles = nnb * nmb;
@@ -970,13 +972,14 @@ static int launch_fused_wm(const double *d_A, int lda, int a_col0, int c_first, 
   const size_t smem = sizeof(double) * (size_t)(BM * (32 + 4) + 32 * B_STRIDE_R) * 3 + 16 * 3;
   const bool ragged = m_valid < BM;
   auto kern = ragged ? k_sigma_fused<WM, true> : k_sigma_fused<WM, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSize attr_dev;
+  int attr_dev_id = 0;
+  if (attr_dev.needs(1, &attr_dev_id)) {
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_fused<WM, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_fused<WM, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_dev.record(attr_dev_id, 1);
   }
   FQEB_REQUIRE(smem <= 227 * 1024, "fused sigma: shared memory budget exceeded");
   const int tiles_per_row = pitch / 64;

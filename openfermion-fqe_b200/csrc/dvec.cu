@@ -560,11 +560,12 @@ int launch_make_coeff(const fqeb_graph *g, const double *d_evec, int64_t lde, in
       if (pad > smem) smem = pad;
     }
   }
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
+  static PerDeviceSize attr_dev;
+  int attr_dev_id = 0;
+  if (smem > 48 * 1024 && attr_dev.needs(smem, &attr_dev_id)) {
     FQEB_CUDA(cudaFuncSetAttribute(k_make_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    attr_smem = smem;
+    attr_dev.record(attr_dev_id, smem);
   }
   k_make_coeff<<<(unsigned)tiles, kTB, smem, st>>>(
       npair, lena, lenb, g->lk[0], g->lk[1], g->d_clistT[0], g->d_clist[1], d_rowmap,

@@ -53,6 +53,25 @@ int upload_finish();
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Kernel attributes (dynamic shared-memory limits) belong to the device: call sites keep one
+// of these as a function-local static and (re)apply their attributes when the requested size
+// exceeds what the CURRENT device has been given so far.
+struct PerDeviceSize {
+  std::atomic<size_t> have[64];
+  PerDeviceSize() {
+    for (auto &h : have) h.store(0);
+  }
+  // true if `want` exceeds the size recorded for the current device (the caller then sets the
+  // attributes and calls record())
+  bool needs(size_t want, int *dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev & 63;
+    return want > have[dev & 63].load();
+  }
+  void record(int dev, size_t want) { have[dev].store(want); }
+};
+
 // scratch set of `stream` for graph g (allocated on first use, thread-safe)
 struct GraphScratch {
   double *small;

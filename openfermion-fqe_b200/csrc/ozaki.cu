@@ -1052,8 +1052,9 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
   const size_t smem = (size_t)OZ_NS * o.kc * 2048 + (o.img_bytes > 2048 ? o.img_bytes : 2048) +
                       (o.np < 128 ? 4096 : 0);
   FQEB_REQUIRE(smem + 1856 <= 227 * 1024, "ozaki: shared memory budget exceeded (%zu bytes)", smem);
-  static size_t attr_bytes = 0;   // dynamic + static shared memory must stay within 227 KB
-  if (smem > attr_bytes) {
+  static PerDeviceSize attr_dev;   // dynamic + static shared memory must stay within 227 KB
+  int attr_dev_id = 0;
+  if (attr_dev.needs(smem, &attr_dev_id)) {
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<false, 0>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<false, 7>,
@@ -1066,7 +1067,7 @@ int launch_ozaki(const fqeb_graph *g, const fqeb_op *op, const void *d_planes,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FQEB_CUDA(cudaFuncSetAttribute(k_sigma_ozaki2<true, 9>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
+    attr_dev.record(attr_dev_id, smem);
   }
   int64_t grid = sm_count();
   if (grid > p.ntiles) grid = p.ntiles;

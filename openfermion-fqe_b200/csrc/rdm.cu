@@ -204,18 +204,13 @@ extern "C" int fqeb_gram_accumulate(int M, int N, int64_t ncols, const double *d
   FQEB_CUDA(cudaMallocAsync((void **)&part, sizeof(double2) * (size_t)nslab * M * N, st));
   if (herm) FQEB_CUDA(cudaMemsetAsync(part, 0, sizeof(double2) * (size_t)nslab * M * N, st));
   const size_t smem = sizeof(double) * (size_t)GR_STAGES * 2 * GR_PANEL;
-  {
-    // function attributes belong to the device (context): set them once per device
-    static std::atomic<uint64_t> attr_set{0};
-    int dev = 0;
-    FQEB_CUDA(cudaGetDevice(&dev));
-    const uint64_t bit = 1ull << (dev & 63);
-    if (!(attr_set.load() & bit)) {
-      FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      // two CTAs of 108 KB per SM: ask for the largest shared-memory carve-out
-      FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr_set.fetch_or(bit);
-    }
+  static PerDeviceSize attr_dev;
+  int attr_dev_id = 0;
+  if (attr_dev.needs(smem, &attr_dev_id)) {
+    FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs of 108 KB per SM: ask for the largest shared-memory carve-out
+    FQEB_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_dev.record(attr_dev_id, smem);
   }
   k_gram<<<dim3((unsigned)tiles, (unsigned)nslab), GR_THREADS, smem, st>>>(
       M, N, ncols, slab, (const double2 *)d_bra, ldb, (const double2 *)d_ket, ldk,
