@@ -313,3 +313,25 @@ def test_spin_block_rotation_golden(golden_dir):
     assert np.array_equal(z["tz_perm"][norb:, norb:], fb[0])
     assert np.allclose(z["tz_low"][norb:, norb:], fb[1], atol=1e-14, rtol=0)
     assert np.allclose(z["tz_upp"][:norb, :norb], fa[2], atol=1e-14, rtol=0)
+
+
+def test_oracle_against_reference_at_norb10(golden_dir):
+    """The numpy restatement against the reference's own outputs at a size beyond the small
+    fixtures (tests/golden/ref_large.npz, norb = 10, half filling: 63 504 determinants): rdm12,
+    plain and transition."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(golden_dir), "..", "openfermion-fqe_b200"))
+    from fqe_b200 import synth
+    z = np.load(os.path.join(golden_dir, "ref_large.npz"))
+    if "rdm10_meta" not in z.files:
+        pytest.skip("rdm10 not in ref_large.npz")
+    n, sz, norb = [int(x) for x in z["rdm10_meta"]]
+    na, nb, la, lb = synth.sector_dims(n, sz, norb)
+    ket = synth.state(la, lb, seed=synth.seed_for(norb, 54))
+    bra = synth.state(la, lb, seed=synth.seed_for(norb, 55))
+    g = O.graph(na, nb, norb)
+    for tag, (r1, r2) in (("rdm10", O.rdm12(g, ket)), ("trdm10", O.rdm12(g, ket, bra))):
+        assert O.rel_err(r1, z[f"{tag}_1"]) < 1e-12, tag
+        flat = np.asarray(r2).reshape(-1)
+        assert O.rel_err(flat[z[f"{tag}_2_idx"]], z[f"{tag}_2_val"]) < 1e-12, tag
+        assert abs(np.linalg.norm(r2) - z[f"{tag}_2_norm"][0]) < 1e-11 * z[f"{tag}_2_norm"][0]
